@@ -1,0 +1,83 @@
+/* rife_b200.h -- C ABI of librife_b200.so, the B200-native replacement for the engine underneath the
+ * reference's `class RIFE` (/root/reference/src/rife.h:11-52).  Plain pointers and sizes only; every entry
+ * point returns 0 on success and a negative code on error, never throws, and is safe to call from several
+ * threads on the same handle (the reference calls RIFE::process concurrently from its `proc` threads,
+ * /root/reference/src/main.cpp:346-366).
+ *
+ * What each entry point replaces:
+ *   rife_b200_device_count   ncnn::get_gpu_count()                       src/main.cpp:782-799
+ *   rife_b200_create         RIFE::RIFE(gpuid, tta, tta_temporal, uhd,   src/rife.cpp:27-47, call site main.cpp:825
+ *                                       num_threads, rife_v2, rife_v4)
+ *   rife_b200_load           RIFE::load(modeldir)                        src/rife.cpp:127-379, call site main.cpp:827
+ *   rife_b200_process        RIFE::process(in0, in1, timestep, out)      src/rife.cpp:381-405, call site main.cpp:360
+ *   rife_b200_destroy        RIFE::~RIFE()                               src/rife.cpp:49-78
+ * Additions for the stream / benchmark path (no reference counterpart; the reference re-uploads per call):
+ *   rife_b200_process_device     same computation with frames already resident in device memory
+ *   rife_b200_process_batch      n independent pairs, pipelined over the handle's streams
+ *   rife_b200_weights_* / rife_b200_load_packed   rank-0 parses + packs the model, the blob is broadcast
+ *                                (NCCL over NVLink by the caller, one process per GPU) and loaded without
+ *                                touching the model directory
+ *
+ * gpuid == -1 (the reference's CPU mode) is rejected: there is no CPU fallback in this library.
+ */
+#ifndef RIFE_B200_H
+#define RIFE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rife_b200 rife_b200_t;
+
+#define RIFE_B200_OK 0
+#define RIFE_B200_ERR_ARG (-1)      /* bad argument (null pointer, w/h <= 0, gpuid < 0, ...) */
+#define RIFE_B200_ERR_DEVICE (-2)   /* no such CUDA device / CUDA runtime failure */
+#define RIFE_B200_ERR_MODEL (-3)    /* model directory unreadable or malformed */
+#define RIFE_B200_ERR_STATE (-4)    /* process before load */
+#define RIFE_B200_ERR_INTERNAL (-5)
+
+int rife_b200_device_count(void);
+
+int rife_b200_create(rife_b200_t** handle, int gpuid, int tta_mode, int tta_temporal_mode, int uhd_mode,
+                     int num_threads /* ignored: kept for signature parity */, int rife_v2, int rife_v4);
+
+/* reads flownet.{param,bin} (+ contextnet / fusionnet unless rife_v4), as the reference does */
+int rife_b200_load(rife_b200_t* handle, const char* modeldir);
+
+/* in0/in1/out: packed RGB u8, HWC, w*h*3 bytes each, caller-owned HOST memory.
+ * timestep == 0 / 1 copies in0 / in1 to out (the reference rebinds the output Mat, src/rife.cpp:3206-3216). */
+int rife_b200_process(rife_b200_t* handle, const unsigned char* in0_rgb, const unsigned char* in1_rgb,
+                      int w, int h, float timestep, unsigned char* out_rgb);
+
+/* same, with all three buffers in DEVICE memory of the handle's GPU; asynchronous work is complete on return */
+int rife_b200_process_device(rife_b200_t* handle, const unsigned char* d_in0_rgb, const unsigned char* d_in1_rgb,
+                             int w, int h, float timestep, unsigned char* d_out_rgb);
+
+/* n independent frame pairs (host memory), same w/h; pairs are pipelined (H2D / compute / D2H overlap) */
+int rife_b200_process_batch(rife_b200_t* handle, int n, const unsigned char* const* in0_rgb,
+                            const unsigned char* const* in1_rgb, int w, int h, const float* timesteps,
+                            unsigned char* const* out_rgb);
+
+/* precision tier: 0 = exact (fp32 CUDA-core path for every layer), 1 = fast (tcgen05 fp16 tensor-core
+ * convolutions with split-precision operands where needed).  Default 1 when the model supports it. */
+int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
+
+/* packed-weights path for multi-GPU loading without re-reading the model directory on every rank */
+int rife_b200_weights_size(rife_b200_t* handle, size_t* bytes);                 /* after load() on rank 0 */
+int rife_b200_weights_export(rife_b200_t* handle, void* host_dst, size_t bytes);
+int rife_b200_load_packed(rife_b200_t* handle, const void* host_src, size_t bytes);
+
+/* kernels launched by this library since process start (bench.py reports it as gpu_launches) */
+unsigned long long rife_b200_launch_count(void);
+
+/* last error message of the handle (thread-unsafe convenience for diagnostics); never NULL */
+const char* rife_b200_last_error(rife_b200_t* handle);
+
+void rife_b200_destroy(rife_b200_t* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIFE_B200_H */

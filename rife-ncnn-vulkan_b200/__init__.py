@@ -1,0 +1,146 @@
+"""rife-ncnn-vulkan_b200 -- host-side mirror of the reference's `class RIFE` (/root/reference/src/rife.h:11-52)
+over the C ABI of librife_b200.so (include/rife_b200.h).  Python is used here only as the test / bench host;
+the drop-in host code for src/main.cpp is the C++ shim in host/ (same ABI).
+
+The directory name is not an importable identifier; load it with `__graft_entry__.load_package()`.
+There is no CPU fallback: constructing RIFE without the built CUDA library raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librife_b200.so")
+
+ERRORS = {0: "ok", -1: "bad argument", -2: "CUDA device error", -3: "model error", -4: "process before load", -5: "internal error"}
+
+_lib = None
+
+
+def lib():
+    """dlopen librife_b200.so once and declare the prototypes of include/rife_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("librife_b200.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.rife_b200_device_count.restype = ci
+    L.rife_b200_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci, ci]
+    L.rife_b200_load.argtypes = [vp, ctypes.c_char_p]
+    L.rife_b200_process.argtypes = [vp, vp, vp, ci, ci, cf, vp]
+    L.rife_b200_process_device.argtypes = [vp, vp, vp, ci, ci, cf, vp]
+    L.rife_b200_process_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ctypes.POINTER(cf), ctypes.POINTER(vp)]
+    L.rife_b200_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    L.rife_b200_weights_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    L.rife_b200_weights_export.argtypes = [vp, vp, ctypes.c_size_t]
+    L.rife_b200_load_packed.argtypes = [vp, vp, ctypes.c_size_t]
+    L.rife_b200_launch_count.restype = ctypes.c_ulonglong
+    L.rife_b200_last_error.argtypes = [vp]
+    L.rife_b200_last_error.restype = ctypes.c_char_p
+    L.rife_b200_destroy.argtypes = [vp]
+    L.rife_b200_destroy.restype = None
+    _lib = L
+    return L
+
+
+EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
+           "rife_b200_process_batch", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
+           "rife_b200_load_packed", "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
+
+
+def family_flags(model_name):
+    """(rife_v2, rife_v4) from the model directory name, as src/main.cpp:658-683 sniffs them."""
+    n = os.path.basename(os.path.normpath(model_name))
+    if n.startswith("rife-v4"):
+        return False, True
+    if n.startswith("rife-v2") or n.startswith("rife-v3"):
+        return True, False
+    return False, False
+
+
+class RifeError(RuntimeError):
+    pass
+
+
+class RIFE:
+    """Same constructor arguments and methods as the reference class (rife.h:14-24)."""
+
+    def __init__(self, gpuid, tta_mode=False, tta_temporal_mode=False, uhd_mode=False, num_threads=1, rife_v2=False, rife_v4=False):
+        self._h = ctypes.c_void_p()
+        self._lib = lib()
+        r = self._lib.rife_b200_create(ctypes.byref(self._h), int(gpuid), int(tta_mode), int(tta_temporal_mode), int(uhd_mode),
+                                       int(num_threads), int(rife_v2), int(rife_v4))
+        if r != 0:
+            self._h = ctypes.c_void_p()
+            raise RifeError("rife_b200_create(gpuid=%d): %s" % (gpuid, ERRORS.get(r, r)))
+
+    def _check(self, r, what):
+        if r != 0:
+            msg = self._lib.rife_b200_last_error(self._h)
+            raise RifeError("%s: %s (%s)" % (what, ERRORS.get(r, r), msg.decode() if msg else ""))
+
+    def load(self, modeldir):
+        self._check(self._lib.rife_b200_load(self._h, os.fsencode(modeldir)), "load(%s)" % modeldir)
+        return 0
+
+    def set_option(self, key, value):
+        self._check(self._lib.rife_b200_set_option(self._h, key.encode(), int(value)), "set_option(%s)" % key)
+
+    def process(self, in0image, in1image, timestep, outimage=None):
+        """in0image/in1image: uint8 arrays (h, w, 3), C-contiguous host memory. Returns outimage."""
+        a = np.ascontiguousarray(in0image, dtype=np.uint8)
+        b = np.ascontiguousarray(in1image, dtype=np.uint8)
+        if a.ndim != 3 or a.shape[2] != 3 or a.shape != b.shape:
+            raise RifeError("process: frames must both be (h, w, 3) uint8")
+        if outimage is None:
+            outimage = np.empty_like(a)
+        if outimage.shape != a.shape or outimage.dtype != np.uint8 or not outimage.flags.c_contiguous:
+            raise RifeError("process: outimage must be a C-contiguous (h, w, 3) uint8 array")
+        h, w = a.shape[:2]
+        self._check(self._lib.rife_b200_process(self._h, a.ctypes.data, b.ctypes.data, w, h, float(timestep), outimage.ctypes.data), "process")
+        return outimage
+
+    def process_ptr(self, in0_ptr, in1_ptr, w, h, timestep, out_ptr, device=False):
+        """Raw-pointer form (host pointers, or device pointers with device=True)."""
+        fn = self._lib.rife_b200_process_device if device else self._lib.rife_b200_process
+        self._check(fn(self._h, in0_ptr, in1_ptr, int(w), int(h), float(timestep), out_ptr), "process_ptr")
+
+    def process_batch_ptr(self, in0_ptrs, in1_ptrs, w, h, timesteps, out_ptrs):
+        n = len(in0_ptrs)
+        VP = ctypes.c_void_p * n
+        ts = (ctypes.c_float * n)(*[float(t) for t in timesteps])
+        self._check(self._lib.rife_b200_process_batch(self._h, n, VP(*in0_ptrs), VP(*in1_ptrs), int(w), int(h), ts, VP(*out_ptrs)), "process_batch")
+
+    def export_weights(self):
+        n = ctypes.c_size_t()
+        self._check(self._lib.rife_b200_weights_size(self._h, ctypes.byref(n)), "weights_size")
+        buf = np.empty(n.value, np.uint8)
+        self._check(self._lib.rife_b200_weights_export(self._h, buf.ctypes.data, n.value), "weights_export")
+        return buf
+
+    def load_packed(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self._lib.rife_b200_load_packed(self._h, blob.ctypes.data, blob.size), "load_packed")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rife_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def launch_count():
+    return int(lib().rife_b200_launch_count())
+
+
+def device_count():
+    return int(lib().rife_b200_device_count())

@@ -1,0 +1,422 @@
+// engine.cu -- see engine.h.  Dataflow restated from /root/reference/src/rife.cpp (line refs per block).
+#include "engine.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "kernels.h"
+
+namespace rife {
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+    cap = bytes;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+Engine::Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v4)
+    : gpuid_(gpuid), tta_(tta), ttat_(tta_temporal), uhd_(uhd), v2_(v2), v4_(v4) {}
+
+Engine::~Engine() {
+    cudaSetDevice(gpuid_);
+    if (st_) cudaStreamSynchronize(st_);
+    for (auto& r : run_) delete r;
+    for (auto& b : u8_) b.release();
+    for (int i = 0; i < 8; i++) { pad0_[i].release(); pad1_[i].release(); tmp_[i].release(); }
+    for (int i = 0; i < 2; i++) { ts_[i].release(); tsr_[i].release(); for (auto& c : ctx_[i]) c.release(); }
+    for (auto& a : flow_) for (auto& b : a) b.release();
+    for (auto& a : flowr_) for (auto& b : a) b.release();
+    for (auto& b : outp_) b.release();
+    for (auto& p : pinned_) if (p) cudaFreeHost(p);
+    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (st_) cudaStreamDestroy(st_);
+    for (auto& s : st_copy_) if (s) cudaStreamDestroy(s);
+}
+
+int Engine::init() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || gpuid_ < 0 || gpuid_ >= n) { last_error = "no such CUDA device"; return -2; }
+    if (cudaSetDevice(gpuid_) != cudaSuccess) { last_error = "cudaSetDevice failed"; return -2; }
+    if (cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking) != cudaSuccess) { last_error = "stream creation failed"; return -2; }
+    for (auto& s : st_copy_) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (auto& e : ev_) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return 0;
+}
+
+static const char* kNetNames[3] = {"flownet", "contextnet", "fusionnet"};
+
+static bool read_file(const std::string& path, std::string& out) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END);
+    long n = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    out.resize((size_t)n);
+    size_t rd = n ? fread(&out[0], 1, (size_t)n, fp) : 0;
+    fclose(fp);
+    return rd == (size_t)n;
+}
+
+// packed model = "RIFEB200" u32 nnets { u64 param_len, u64 bin_len, param bytes, bin bytes }*
+int Engine::load(const std::string& modeldir) {
+    int nn = v4_ ? 1 : 3;  // rife.cpp:158-163
+    std::string blob = "RIFEB200";
+    uint32_t n32 = (uint32_t)nn;
+    blob.append((const char*)&n32, 4);
+    for (int i = 0; i < nn; i++) {
+        std::string p, b;
+        if (!read_file(modeldir + "/" + kNetNames[i] + ".param", p) || !read_file(modeldir + "/" + kNetNames[i] + ".bin", b)) {
+            last_error = "cannot read " + modeldir + "/" + kNetNames[i] + ".{param,bin}";
+            return -3;
+        }
+        uint64_t pl = p.size(), bl = b.size();
+        blob.append((const char*)&pl, 8);
+        blob.append((const char*)&bl, 8);
+        blob += p;
+        blob += b;
+    }
+    return load_packed(blob.data(), blob.size());
+}
+
+int Engine::load_packed(const void* data, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    cudaSetDevice(gpuid_);
+    const char* p = (const char*)data;
+    if (bytes < 12 || memcmp(p, "RIFEB200", 8)) { last_error = "bad packed model"; return -3; }
+    uint32_t nn;
+    memcpy(&nn, p + 8, 4);
+    if (nn != (uint32_t)(v4_ ? 1 : 3)) { last_error = "packed model does not match the model family flags"; return -3; }
+    size_t pos = 12;
+    for (uint32_t i = 0; i < nn; i++) {
+        uint64_t pl, bl;
+        if (pos + 16 > bytes) { last_error = "truncated packed model"; return -3; }
+        memcpy(&pl, p + pos, 8);
+        memcpy(&bl, p + pos + 8, 8);
+        pos += 16;
+        if (pos + pl + bl > bytes) { last_error = "truncated packed model"; return -3; }
+        std::string ptxt(p + pos, (size_t)pl), bbin(p + pos + pl, (size_t)bl);
+        pos += pl + bl;
+        std::string err;
+        nets_[i] = Net();
+        if (parse_net(ptxt, bbin, kNetNames[i], nets_[i], err)) { last_error = err; return -3; }
+        delete run_[i];
+        run_[i] = new NetRunner();
+        if (run_[i]->init(&nets_[i], err)) { last_error = err; return -3; }
+    }
+    packed_.assign(p, bytes);
+    loaded_ = true;
+    return 0;
+}
+
+int Engine::set_option(const std::string& key, int value) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (key == "precision") { precision_ = value; return 0; }
+    if (key == "fuse") { for (auto& r : run_) if (r) r->fuse = value != 0; return 0; }
+    last_error = "unknown option " + key;
+    return -1;
+}
+
+Tensor Engine::keep(const Tensor& t, DevBuf& b, cudaStream_t st) {
+    Tensor o = t;
+    b.ensure(t.count() * sizeof(float));
+    cudaMemcpyAsync(b.p, t.p, t.count() * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    o.p = b.f();
+    return o;
+}
+
+int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out) {
+    if (!in0 || !in1 || !out || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
+    if (!loaded_) { last_error = "process before load"; return -4; }
+    size_t n = (size_t)w * h * 3;
+    if (t == 0.f) { if (out != in0) memcpy(out, in0, n); return 0; }  // rife.cpp:3206-3216
+    if (t == 1.f) { if (out != in1) memcpy(out, in1, n); return 0; }
+    std::lock_guard<std::mutex> lk(mu_);
+    cudaSetDevice(gpuid_);
+    for (int i = 0; i < 3; i++)
+        if (u8_[i].ensure(n)) { last_error = "cudaMalloc failed"; return -2; }
+    cudaMemcpyAsync(u8_[0].p, in0, n, cudaMemcpyHostToDevice, st_);
+    cudaMemcpyAsync(u8_[1].p, in1, n, cudaMemcpyHostToDevice, st_);
+    int r = run_device(u8_[0].u8(), u8_[1].u8(), w, h, t, u8_[2].u8(), st_);
+    if (r) return r;
+    cudaMemcpyAsync(out, u8_[2].p, n, cudaMemcpyDeviceToHost, st_);
+    cudaError_t e = cudaStreamSynchronize(st_);
+    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out) {
+    if (!d_in0 || !d_in1 || !d_out || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
+    if (!loaded_) { last_error = "process before load"; return -4; }
+    size_t n = (size_t)w * h * 3;
+    std::lock_guard<std::mutex> lk(mu_);
+    cudaSetDevice(gpuid_);
+    if (t == 0.f || t == 1.f) {
+        cudaMemcpyAsync(d_out, t == 0.f ? d_in0 : d_in1, n, cudaMemcpyDeviceToDevice, st_);
+    } else {
+        int r = run_device(d_in0, d_in1, w, h, t, d_out, st_);
+        if (r) return r;
+    }
+    cudaError_t e = cudaStreamSynchronize(st_);
+    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+// Pipelined stream path: pair i+1 uploads while pair i computes and pair i-1 downloads (pinned host memory
+// makes the copies truly asynchronous; pageable memory still works, the driver then stages synchronously).
+int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out) {
+    if (n < 0 || !in0 || !in1 || !out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
+    if (!loaded_) { last_error = "process before load"; return -4; }
+    size_t nb = (size_t)w * h * 3;
+    std::lock_guard<std::mutex> lk(mu_);
+    cudaSetDevice(gpuid_);
+    for (auto& b : u8_)
+        if (b.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
+    // events: ev_[0..1] h2d done (per set), ev_[2..3] compute done, ev_[4..5] d2h done
+    for (int i = 0; i < n; i++) {
+        int s = i & 1;
+        if (!in0[i] || !in1[i] || !out[i]) { last_error = "null frame pointer"; return -1; }
+        if (ts[i] == 0.f || ts[i] == 1.f) {
+            // copies must not overtake queued work that reads/writes out[] ordering is per pair, so a host copy is safe after sync
+            cudaStreamSynchronize(st_copy_[1]);
+            memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);
+            continue;
+        }
+        uint8_t* d0 = u8_[s * 3 + 0].u8();
+        uint8_t* d1 = u8_[s * 3 + 1].u8();
+        uint8_t* dout = u8_[s * 3 + 2].u8();
+        if (i >= 2) cudaStreamWaitEvent(st_copy_[0], ev_[2 + s], 0);  // inputs of set s free once its compute finished
+        cudaMemcpyAsync(d0, in0[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
+        cudaMemcpyAsync(d1, in1[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
+        cudaEventRecord(ev_[s], st_copy_[0]);
+        cudaStreamWaitEvent(st_, ev_[s], 0);
+        if (i >= 2) cudaStreamWaitEvent(st_, ev_[4 + s], 0);  // output buffer of set s downloaded
+        int r = run_device(d0, d1, w, h, ts[i], dout, st_);
+        if (r) return r;
+        cudaEventRecord(ev_[2 + s], st_);
+        cudaStreamWaitEvent(st_copy_[1], ev_[2 + s], 0);
+        cudaMemcpyAsync(out[i], dout, nb, cudaMemcpyDeviceToHost, st_copy_[1]);
+        cudaEventRecord(ev_[4 + s], st_copy_[1]);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(st_copy_[0]);
+    cudaError_t e1 = cudaStreamSynchronize(st_);
+    cudaError_t e2 = cudaStreamSynchronize(st_copy_[1]);
+    cudaError_t e = e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
+    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+int Engine::run_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
+    int r = v4_ ? run_v4(d_in0, d_in1, w, h, t, d_out, st) : run_v1v2(d_in0, d_in1, w, h, d_out, st);
+    if (r) return r;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+typedef std::vector<std::pair<std::string, Tensor>> Inputs;
+
+// ---- rife-v4 / v4.6: rife.cpp:3204-4401 -------------------------------------------------------------------
+int Engine::run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
+    const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;  // rife.cpp:3229-3230
+    const size_t plane = (size_t)wp * hp;
+    NetRunner& F = *run_[0];
+    std::string err;
+    std::vector<Tensor> o;
+    const int nti = tta_ ? 8 : 1;
+    Tensor I0[8], I1[8], T[2], TR[2];
+    for (int ti = 0; ti < nti; ti++) {
+        if (pad0_[ti].ensure(3 * plane * 4) || pad1_[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
+        launch_preproc(d_in0, w, h, pad0_[ti].f(), wp, hp, ti, st);  // rife.cpp:4152-4211 / 3253-3413
+        launch_preproc(d_in1, w, h, pad1_[ti].f(), wp, hp, ti, st);
+        int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
+        I0[ti] = Tensor::chw(pad0_[ti].f(), 3, th, tw);
+        I1[ti] = Tensor::chw(pad1_[ti].f(), 3, th, tw);
+    }
+    ts_[0].ensure(plane * 4);
+    launch_fill(ts_[0].f(), plane, t, st);  // full padded plane, rife.cpp:4213-4214
+    T[0] = Tensor::chw(ts_[0].f(), 1, hp, wp);
+    T[1] = Tensor::chw(ts_[0].f(), 1, wp, hp);  // rife.cpp:3313-3316 (same constant, transposed extent)
+    if (ttat_) {
+        tsr_[0].ensure(plane * 4);
+        launch_fill(tsr_[0].f(), plane, 1.f - t, st);
+        TR[0] = Tensor::chw(tsr_[0].f(), 1, hp, wp);
+        TR[1] = Tensor::chw(tsr_[0].f(), 1, wp, hp);
+    }
+    static const char* kFlow[4] = {"flow0", "flow1", "flow2", "flow3"};
+
+    if (!tta_ && !ttat_) {
+        // rife.cpp:4345-4351
+        Inputs in = {{"in0", I0[0]}, {"in1", I1[0]}, {"in2", T[0]}};
+        if (F.run(in, {"out0"}, o, st, err)) { last_error = err; return -5; }
+        const float* ins[1] = {o[0].p};
+        launch_postproc(ins, nullptr, 1, wp, hp, d_out, w, h, 1, st);  // rife.cpp:4375-4398
+        return 0;
+    }
+
+    Tensor fl[4][8], flr[4][8];
+    for (int fi = 0; fi < 4; fi++) {
+        for (int ti = 0; ti < nti; ti++) {
+            {   // rife.cpp:3432-3451 / 4233-4252: inject the already merged flow0..fi-1, extract flow<fi>
+                Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
+                for (int k = 0; k < fi; k++) in.push_back({kFlow[k], fl[k][ti]});
+                if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
+                fl[fi][ti] = keep(o[0], flow_[fi][ti], st);
+            }
+            if (ttat_) {
+                Inputs in = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
+                for (int k = 0; k < fi; k++) in.push_back({kFlow[k], flr[k][ti]});
+                if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
+                flr[fi][ti] = keep(o[0], flowr_[fi][ti], st);
+                // rife.cpp:3476-3512 / 4277-4312
+                launch_temporal_merge_v2(fl[fi][ti].p, flr[fi][ti].p, (size_t)fl[fi][ti].h * fl[fi][ti].w, 1, st);
+            }
+        }
+        if (tta_) {  // rife.cpp:3515-3668 (+ reversed set :3670-3823)
+            float* f8[8];
+            for (int ti = 0; ti < 8; ti++) f8[ti] = fl[fi][ti].p;
+            launch_flow_tta_avg(f8, 5, fl[fi][0].w, fl[fi][0].h, st);
+            if (ttat_) {
+                for (int ti = 0; ti < 8; ti++) f8[ti] = flr[fi][ti].p;
+                launch_flow_tta_avg(f8, 5, fl[fi][0].w, fl[fi][0].h, st);
+            }
+        }
+    }
+    const float* ins[16];
+    int orients[16];
+    for (int ti = 0; ti < nti; ti++) {
+        Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
+        for (int k = 0; k < 4; k++) in.push_back({kFlow[k], fl[k][ti]});
+        if (F.run(in, {"out0"}, o, st, err)) { last_error = err; return -5; }
+        ins[ti] = keep(o[0], outp_[ti], st).p;
+        orients[ti] = ti;
+        if (ttat_) {
+            Inputs inr = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
+            for (int k = 0; k < 4; k++) inr.push_back({kFlow[k], flr[k][ti]});
+            if (F.run(inr, {"out0"}, o, st, err)) { last_error = err; return -5; }
+            ins[nti + ti] = keep(o[0], outp_[8 + ti], st).p;
+            orients[nti + ti] = ti;
+        }
+    }
+    if (tta_) launch_postproc(ins, orients, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, st);  // rife.cpp:4060-4144
+    else launch_postproc(ins, nullptr, 2, wp, hp, d_out, w, h, 1, st);                    // rife.cpp:4356-4371
+    return 0;
+}
+
+// ---- rife / rife-HD / rife-UHD / rife-anime (v1), rife-v2.x / v3.x (v2): rife.cpp:1214-2460 ----------------
+int Engine::run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st) {
+    const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
+    const size_t plane = (size_t)wp * hp;
+    NetRunner& F = *run_[0];
+    NetRunner& C = *run_[1];
+    NetRunner& U = *run_[2];
+    std::string err;
+    std::vector<Tensor> o;
+    const int nti = tta_ ? 8 : 1;
+    Tensor I0[8], I1[8];
+    for (int ti = 0; ti < nti; ti++) {
+        if (pad0_[ti].ensure(3 * plane * 4) || pad1_[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
+        launch_preproc(d_in0, w, h, pad0_[ti].f(), wp, hp, ti, st);
+        launch_preproc(d_in1, w, h, pad1_[ti].f(), wp, hp, ti, st);
+        int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
+        I0[ti] = Tensor::chw(pad0_[ti].f(), 3, th, tw);
+        I1[ti] = Tensor::chw(pad1_[ti].f(), 3, th, tw);
+    }
+    // flownet(a, b) -> flow at half resolution; uhd: rife.cpp:2212-2229
+    auto flownet = [&](const Tensor& a, const Tensor& b, DevBuf& dst, Tensor& flow) -> int {
+        if (uhd_) {
+            Tensor ad = Tensor::chw(nullptr, 3, (int)(a.h * 0.5f), (int)(a.w * 0.5f)), bd = ad;
+            tmp_[0].ensure(ad.count() * 4);
+            tmp_[1].ensure(ad.count() * 4);
+            ad.p = tmp_[0].f();
+            bd.p = tmp_[1].f();
+            launch_interp_bilinear(a.p, 3, a.h, a.w, ad.p, ad.h, ad.w, st);
+            launch_interp_bilinear(b.p, 3, b.h, b.w, bd.p, bd.h, bd.w, st);
+            Inputs in = {{"input0", ad}, {"input1", bd}};
+            if (F.run(in, {"flow"}, o, st, err)) { last_error = err; return -5; }
+            Tensor fd = o[0];
+            flow = Tensor::chw(nullptr, fd.c, (int)(fd.h * 2.f), (int)(fd.w * 2.f));
+            dst.ensure(flow.count() * 4);
+            flow.p = dst.f();
+            launch_interp_bilinear(fd.p, fd.c, fd.h, fd.w, flow.p, flow.h, flow.w, st);
+            launch_unary(flow.p, flow.p, flow.count(), U_MUL_S, 2.f, 0.f, st);
+        } else {
+            Inputs in = {{"input0", a}, {"input1", b}};
+            if (F.run(in, {"flow"}, o, st, err)) { last_error = err; return -5; }
+            flow = keep(o[0], dst, st);
+        }
+        return 0;
+    };
+    Tensor fl[8], flr[8];
+    for (int ti = 0; ti < nti; ti++)
+        if (flownet(I0[ti], I1[ti], flow_[0][ti], fl[ti])) return -5;
+    auto merge = [&](int ti) {
+        size_t n = (size_t)fl[ti].h * fl[ti].w;
+        if (v2_) launch_temporal_merge_v2(fl[ti].p, flr[ti].p, n, 0, st);  // rife.cpp:2285-2306
+        else launch_temporal_merge_v1(fl[ti].p, flr[ti].p, n, st);         // rife.cpp:2307-2319
+    };
+    if (ttat_)
+        for (int ti = 0; ti < nti; ti++) {
+            if (flownet(I1[ti], I0[ti], flowr_[0][ti], flr[ti])) return -5;
+            merge(ti);
+        }
+    if (tta_) {  // rife.cpp:1541-1719, reversed :1721-1896, second merge :1898-1949
+        float* f8[8];
+        for (int ti = 0; ti < 8; ti++) f8[ti] = fl[ti].p;
+        launch_flow_tta_avg(f8, v2_ ? 4 : 2, fl[0].w, fl[0].h, st);
+        if (ttat_) {
+            for (int ti = 0; ti < 8; ti++) f8[ti] = flr[ti].p;
+            launch_flow_tta_avg(f8, v2_ ? 4 : 2, fl[0].w, fl[0].h, st);
+            for (int ti = 0; ti < 8; ti++) merge(ti);
+        }
+    }
+    static const char* kCtx[4] = {"f1", "f2", "f3", "f4"};
+    const float* ins[16];
+    int orients[16];
+    for (int ti = 0; ti < nti; ti++) {
+        Tensor c0[4], c1[4];
+        Tensor f0 = fl[ti], f1 = fl[ti];
+        if (v2_) {  // Slice 4 -> 2 + 2, rife.cpp:2322-2330
+            f0.c = 2;
+            f1.c = 2;
+            f1.p = fl[ti].p + 2 * (size_t)fl[ti].h * fl[ti].w;
+        }
+        {   // rife.cpp:2335-2351
+            Inputs in = {{"input.1", I0[ti]}, {"flow.0", f0}};
+            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
+            for (int k = 0; k < 4; k++) c0[k] = keep(o[k], ctx_[0][k], st);
+        }
+        {   // rife.cpp:2352-2368
+            Inputs in = {{"input.1", I1[ti]}, {v2_ ? "flow.0" : "flow.1", f1}};
+            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
+            for (int k = 0; k < 4; k++) c1[k] = keep(o[k], ctx_[1][k], st);
+        }
+        {   // rife.cpp:2372-2388
+            Inputs in = {{"img0", I0[ti]}, {"img1", I1[ti]}, {"flow", fl[ti]}, {"3", c0[0]}, {"4", c0[1]}, {"5", c0[2]}, {"6", c0[3]},
+                         {"7", c1[0]}, {"8", c1[1]}, {"9", c1[2]}, {"10", c1[3]}};
+            if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
+            ins[ti] = (tta_ || ttat_) ? keep(o[0], outp_[ti], st).p : o[0].p;
+            orients[ti] = ti;
+        }
+        if (ttat_) {  // rife.cpp:2391-2409
+            Inputs in = {{"img0", I1[ti]}, {"img1", I0[ti]}, {"flow", flr[ti]}, {"3", c1[0]}, {"4", c1[1]}, {"5", c1[2]}, {"6", c1[3]},
+                         {"7", c0[0]}, {"8", c0[1]}, {"9", c0[2]}, {"10", c0[3]}};
+            if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
+            ins[nti + ti] = keep(o[0], outp_[8 + ti], st).p;
+            orients[nti + ti] = ti;
+        }
+    }
+    if (tta_) launch_postproc(ins, orients, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, st);
+    else launch_postproc(ins, nullptr, ttat_ ? 2 : 1, wp, hp, d_out, w, h, 1, st);
+    return 0;
+}
+
+}  // namespace rife
