@@ -41,6 +41,10 @@ def _cpu_flags():
 def ref_binary():
     """Path of the reference-oracle executable usable on this host, or None."""
     fl = _cpu_flags()
+    forced = os.environ.get("RIFE_ORACLE_ISA")
+    if forced:
+        p = os.path.join(REF_DIR, "ref_rife_" + forced)
+        return p if os.path.exists(p) else None
     cands = []
     if {"avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512cd"} <= fl:
         cands.append("ref_rife_avx512")

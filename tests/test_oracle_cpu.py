@@ -1,0 +1,52 @@
+"""Pins the oracle (no GPU): the C++ restatement in oracle/ must reproduce the committed golden frames, which
+were produced by oracle/_ref = the reference's own CPU functions + its vendored ncnn (tests/golden/make_golden.py).
+Two valid CPU builds of the reference differ by 1 LSB on ~1e-4 of the values, hence the tolerance."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "golden.json")))
+ARRAYS = np.load(os.path.join(GOLD, "golden.npz"))
+
+FAST = ["v46_plain_128x96", "v46_plain_100x70_cpu_crop_quirk", "v46_t025_128x96", "v46_tta_96x64", "v46_temporal_96x64",
+        "v46_tta_temporal_96x64", "v46_large_motion_160x96", "v4_t075_128x96", "v23_plain_128x96", "v23_uhd_128x128", "anime_plain_128x96"]
+
+
+def _inputs(name):
+    m = MANIFEST[name]
+    a, b = parity.synth.pair(m["w"], m["h"], **m["synth_kwargs"])
+    assert hashlib.sha256(a.tobytes() + b.tobytes()).hexdigest() == m["in_sha256"], "synthetic frame generator drifted"
+    return m, a, b
+
+
+def test_golden_file_is_intact():
+    for name, m in MANIFEST.items():
+        assert hashlib.sha256(ARRAYS[name].tobytes()).hexdigest() == m["out_sha256"], name
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_port_reproduces_golden(name):
+    if parity.port_binary() is None:
+        pytest.skip("oracle/build/oracle_rife not built")
+    m, a, b = _inputs(name)
+    if parity.model_dir(m["model"]) is None:
+        pytest.skip("model not available")
+    out, _ = parity.run_oracle(m["model"], a, b, which="port", **m["oracle_kwargs"])
+    res = parity.compare(out, ARRAYS[name])
+    assert res["max_abs_diff"] <= 1 and res["share_ne"] < 2e-3, res
+
+
+@pytest.mark.parametrize("name", ["v46_plain_128x96", "v23_plain_128x96", "anime_tta_temporal_96x64"])
+def test_reference_binary_reproduces_golden(name):
+    if parity.ref_binary() is None:
+        pytest.skip("oracle/_ref not built on this host")
+    m, a, b = _inputs(name)
+    out, _ = parity.run_oracle(m["model"], a, b, which="ref", **m["oracle_kwargs"])
+    res = parity.compare(out, ARRAYS[name])
+    assert res["max_abs_diff"] <= 1 and res["share_ne"] < 2e-3, res
