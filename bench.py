@@ -1,0 +1,284 @@
+#!/usr/bin/env python3
+"""bench.py -- interpolated frames/sec of the RIFE hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of PAIRS_PER_STEP synthetic frame pairs (rife-v4.6, t = 0.5).
+  value     whole-job frames/s with the frames resident in HBM (rife_b200_process_device), CUDA-event timed on the
+            stream the kernels are launched on, max over ranks.
+  e2e       the same metric through the reference-facing call with HOST buffers (rife_b200_process_batch, pinned
+            memory): H2D of two u8 frames + D2H of one per pair inside the timed region.
+  roofline  the dominant kernel (tcgen05 conv3x3 64->64 at quarter resolution, 44 % of the model's FLOPs) timed alone
+            with CUDA events; achieved = 2*9*Cin*Cout*H*W FLOP per launch / time; peak = measured cuBLAS bf16 TF/s.
+  cpu_baseline  the reference's own CPU path (oracle/_ref: its rife.cpp CPU functions + vendored ncnn) on the host
+            cores, bounded sample, rank 0 only.
+--impl reference times that CPU path alone on the same workload (the driver computes the ratio).
+Multi-GPU: one process per GPU (torchrun); frame pairs are independent, so ranks share nothing after rank 0
+broadcasts the packed model over NCCL; scaling is weak (fixed pairs per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {"1080p": (1920, 1080, "rife-v4.6 1920x1080 synthetic frame-pair stream (BASELINE configs[1])"),
+             "4k": (3840, 2160, "rife-v4.6 3840x2160 UHD-flag stream (BASELINE configs[2]; -u is a no-op for v4 nets)")}
+GFLOP_PER_FRAME = {"1080p": 175.2, "4k": 701.0}
+PAIRS_PER_STEP = 8
+MODEL = "rife-v4.6"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, idx):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self.stop_flag = idx, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_fps(workload, frames, threads=None, warmup=1):
+    """Times the reference's CPU path on `frames` frames of the workload; returns dict for the JSON line."""
+    import parity
+    w, h, _ = WORKLOADS[workload]
+    a, b = parity.synth.pair(w, h)
+    ncpu = os.cpu_count() or 1
+    threads = threads or min(ncpu, 64)
+    _, info = parity.run_oracle(MODEL, a, b, 0.5, threads=threads, repeat=frames, warmup=warmup)
+    secs = info["sec_per_frame"]
+    fps = len(secs) / sum(secs)
+    return {"value": fps, "unit": "frames/s", "cores": threads, "kind": info["kind"],
+            "sample": "%d frames of %s after %d warm-up (%.2f s/frame)" % (len(secs), workload, warmup, sum(secs) / len(secs))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, h, desc = WORKLOADS[args.workload]
+    frames = 2 if args.workload == "1080p" else 1
+    t0 = time.time()
+    per_step = []
+    base = None
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_fps(args.workload, 1, warmup=0)
+    for _ in range(args.steps):
+        base = cpu_reference_fps(args.workload, frames, warmup=0)
+        per_step.append(base["value"])
+        if time.time() - t0 > 240:
+            break
+    fps = sum(per_step) / len(per_step)
+    base["value"] = fps
+    base["sample"] = "each step = %d frames of %s; %d steps" % (frames, args.workload, len(per_step))
+    line = {"impl": "reference", "metric": "interpolated frames/sec (rife-v4.6)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(per_step), "warmup": args.warmup, "ms_per_step": 1000.0 * frames / fps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "timestep": 0.5},
+            "cpu_baseline": base, "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as g
+    import parity
+    pkg = g.load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w, h, desc = WORKLOADS[args.workload]
+    md = parity.model_dir(MODEL)
+    if md is None:
+        raise SystemExit("model %s not found (oracle/_ref/models or tests/models)" % MODEL)
+    v2, v4 = pkg.family_flags(MODEL)
+    eng = pkg.RIFE(local, False, False, args.workload == "4k", 1, v2, v4)
+    # weights: rank 0 reads the model directory, everyone else receives the packed blob over NCCL (NVLink)
+    if world > 1:
+        if rank == 0:
+            eng.load(md)
+            blob = torch.from_numpy(eng.export_weights()).cuda()
+            n = torch.tensor([blob.numel()], dtype=torch.int64, device="cuda")
+        else:
+            n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        dist.broadcast(n, 0)
+        if rank != 0:
+            blob = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(blob, 0)
+        if rank != 0:
+            eng.load_packed(blob.cpu().numpy())
+    else:
+        eng.load(md)
+    eng.set_option("precision", args.precision)
+
+    # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
+    nframes = PAIRS_PER_STEP + 1
+    frames = [parity.synth.frame(k, w, h, seed=rank) for k in range(nframes)]
+    host = [torch.from_numpy(f).pin_memory() for f in frames]
+    dev = [t.cuda(non_blocking=True) for t in host]
+    out_dev = [torch.empty_like(dev[0]) for _ in range(PAIRS_PER_STEP)]
+    out_host = [torch.empty_like(host[0]).pin_memory() for _ in range(PAIRS_PER_STEP)]
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_option("async", 1)
+    torch.cuda.synchronize()
+
+    def step_device():
+        for i in range(PAIRS_PER_STEP):
+            eng.process_ptr(dev[i].data_ptr(), dev[i + 1].data_ptr(), w, h, 0.5, out_dev[i].data_ptr(), device=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        launches0 = pkg.launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            l2_flush.zero_()  # flush L2 between timed iterations (outside the event bracket)
+            ev[k][0].record(stream)
+            step_device()
+            ev[k][1].record(stream)
+        barrier()
+        launches = pkg.launch_count() - launches0
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    t_local = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_total = float(t_local.item())
+    value = world * PAIRS_PER_STEP * args.steps / (ms_total / 1000.0)
+
+    # e2e: host buffers through the batch call (H2D + compute + D2H pipelined inside the library)
+    eng.set_stream(0)
+    eng.set_option("async", 0)
+    in0 = [t.data_ptr() for t in host[:PAIRS_PER_STEP]]
+    in1 = [t.data_ptr() for t in host[1:PAIRS_PER_STEP + 1]]
+    outp = [t.data_ptr() for t in out_host]
+    ts = [0.5] * PAIRS_PER_STEP
+    for _ in range(2):
+        eng.process_batch_ptr(in0, in1, w, h, ts, outp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.process_batch_ptr(in0, in1, w, h, ts, outp)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * PAIRS_PER_STEP * args.steps / float(t_e2e.item())
+    clocks = sampler.summary()
+    checksum = int(out_host[0].to(torch.int64).sum().item())
+
+    # roofline of the dominant kernel: conv3x3 64->64 (+res +leaky) at (h/4) x (w/4), split-fp16 operands count double
+    burst, sustained, hbm, how = measured_peaks()
+    hp, wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    ch, cw = hp // 4, wp // 4
+    split = 1 if args.precision == 1 else 0
+    iters = 20
+    with torch.cuda.stream(stream):
+        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, 3, gpuid=local)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, iters, gpuid=local)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / iters
+    flop = 2.0 * 9 * 64 * 64 * ch * cw  # algorithmic FLOPs of the layer; the hi+lo split issues 2x this on the tensor pipe
+    achieved = flop / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                "kernel": "tc_conv3x3_kernel<64,4,3> %dx%d" % (cw, ch), "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
+                "tensor_issue_multiplier": 2 if split else 1}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu = cpu_reference_fps(args.workload, 2 if args.workload == "1080p" else 1)
+            except Exception as e:  # the oracle binary did not travel / wrong ISA: report, do not fake
+                cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+        nb = w * h * 3
+        line = {"metric": "interpolated frames/sec (rife-v4.6)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
+                "data": "synthetic",
+                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision,
+                           "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
+                "gflop_per_frame": GFLOP_PER_FRAME[args.workload],
+                "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0,
+                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": 2 * nb * PAIRS_PER_STEP, "d2h_bytes_per_step": nb * PAIRS_PER_STEP},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "out_checksum": checksum}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -69,6 +69,24 @@ int rife_b200_weights_size(rife_b200_t* handle, size_t* bytes);                 
 int rife_b200_weights_export(rife_b200_t* handle, void* host_dst, size_t bytes);
 int rife_b200_load_packed(rife_b200_t* handle, const void* host_src, size_t bytes);
 
+/* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the handle's own
+ * stream) so a caller can bracket it with its own events.  option "async" = 1 makes rife_b200_process_device return
+ * without synchronising that stream. */
+int rife_b200_set_stream(rife_b200_t* handle, void* cuda_stream);
+
+/* Launches the tcgen05 conv3x3 (cin -> cout, h x w, bias + residual + leaky) `iters` times on `cuda_stream` with
+ * device-resident synthetic data and returns; used by bench.py to time the dominant kernel with its own events. */
+int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
+
+/* Diagnostics: runs ONE convolution layer through the tcgen05 tensor-core kernel and through the fp32 CUDA-core
+ * kernel on the same data and returns both results (planar fp32, host memory) so a test can compare them.
+ * mode 0: conv3x3 s1 p1 (+bias, + optional residual `res`, + leaky `slope`), in [cin][h][w] -> out [cout][h][w]
+ * mode 1: deconv4x4 s2 p1 (+bias) followed by PixelShuffle(ps), in [cin][h][w] -> out [cout/(ps*ps)][2h*ps][2w*ps]
+ * split != 0 stores activations as split-fp16 (hi+lo) for the tensor-core path. */
+int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w, int split, int ps, const float* in,
+                            const float* weight, const float* bias, const float* res, float slope, float* out_tc,
+                            float* out_ref);
+
 /* kernels launched by this library since process start (bench.py reports it as gpu_launches) */
 unsigned long long rife_b200_launch_count(void);
 

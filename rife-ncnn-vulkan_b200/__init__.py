@@ -38,6 +38,9 @@ def lib():
     L.rife_b200_weights_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     L.rife_b200_weights_export.argtypes = [vp, vp, ctypes.c_size_t]
     L.rife_b200_load_packed.argtypes = [vp, vp, ctypes.c_size_t]
+    L.rife_b200_set_stream.argtypes = [vp, vp]
+    L.rife_b200_bench_conv.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci]
+    L.rife_b200_selftest_conv.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, cf, vp, vp]
     L.rife_b200_launch_count.restype = ctypes.c_ulonglong
     L.rife_b200_last_error.argtypes = [vp]
     L.rife_b200_last_error.restype = ctypes.c_char_p
@@ -49,7 +52,8 @@ def lib():
 
 EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
            "rife_b200_process_batch", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
-           "rife_b200_load_packed", "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
+           "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv",
+           "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
 
 
 def family_flags(model_name):
@@ -115,6 +119,9 @@ class RIFE:
         ts = (ctypes.c_float * n)(*[float(t) for t in timesteps])
         self._check(self._lib.rife_b200_process_batch(self._h, n, VP(*in0_ptrs), VP(*in1_ptrs), int(w), int(h), ts, VP(*out_ptrs)), "process_batch")
 
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.rife_b200_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)), "set_stream")
+
     def export_weights(self):
         n = ctypes.c_size_t()
         self._check(self._lib.rife_b200_weights_size(self._h, ctypes.byref(n)), "weights_size")
@@ -138,9 +145,36 @@ class RIFE:
             pass
 
 
+def bench_conv(cuda_stream_ptr, cin, cout, h, w, split, iters, gpuid=0):
+    rc = lib().rife_b200_bench_conv(gpuid, ctypes.c_void_p(cuda_stream_ptr), cin, cout, h, w, int(split), iters)
+    if rc != 0:
+        raise RifeError("bench_conv failed: %d" % rc)
+
+
 def launch_count():
     return int(lib().rife_b200_launch_count())
 
 
 def device_count():
     return int(lib().rife_b200_device_count())
+
+
+def selftest_conv(mode, x, weight, bias, res=None, slope=0.2, split=True, ps=2, gpuid=0):
+    """Runs one layer through the tcgen05 kernel and the fp32 CUDA-core kernel; returns (out_tc, out_ref)."""
+    x = np.ascontiguousarray(x, np.float32)
+    weight = np.ascontiguousarray(weight, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    cin, h, w = x.shape
+    cout = weight.shape[0]
+    if mode == 0:
+        oshape = (cout, h, w)
+    else:
+        oshape = (cout // (ps * ps), 2 * h * ps, 2 * w * ps)
+    o1 = np.zeros(oshape, np.float32)
+    o2 = np.zeros(oshape, np.float32)
+    r = None if res is None else np.ascontiguousarray(res, np.float32)
+    rc = lib().rife_b200_selftest_conv(gpuid, mode, cin, cout, h, w, int(split), ps, x.ctypes.data, weight.ctypes.data, bias.ctypes.data,
+                                       None if r is None else r.ctypes.data, float(slope), o1.ctypes.data, o2.ctypes.data)
+    if rc != 0:
+        raise RifeError("selftest_conv failed: %d" % rc)
+    return o1, o2

@@ -135,3 +135,156 @@ void rife_b200_destroy(rife_b200_t* h) {
 }
 
 }  // extern "C"
+
+// ---- diagnostics ---------------------------------------------------------------------------------------------
+#include <vector>
+
+#include "tc_conv.h"
+
+extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w, int split, int ps, const float* in, const float* weight,
+                                       const float* bias, const float* res, float slope, float* out_tc, float* out_ref) {
+    GUARD_BEGIN
+    using namespace rife;
+    if (!in || !weight || !bias || !out_tc || !out_ref || cin % 16 || cin <= 0 || cout <= 0 || h <= 0 || w <= 0) return RIFE_B200_ERR_ARG;
+    if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
+    cudaStream_t st = 0;
+    const size_t hw = (size_t)h * w;
+    const int kk = mode == 0 ? 9 : 16;
+    // fp16-exact weights, as in the model files
+    std::vector<float> wq((size_t)cout * cin * kk);
+    for (size_t i = 0; i < wq.size(); i++) wq[i] = __half2float(__float2half_rn(weight[i]));
+    int N, ocs = 0;
+    std::vector<uint16_t> wpk;
+    if (mode == 0) {
+        N = (cout + 15) / 16 * 16;
+        if (N != cout) return RIFE_B200_ERR_ARG;
+        pack_conv3x3_weights(wq.data(), cout, cin, N, wpk);
+    } else {
+        ocs = (cout + 7) / 8 * 8;
+        N = 4 * ocs;
+        pack_deconv4x4_weights(wq.data(), cout, cin, ocs, N, wpk);
+    }
+    std::vector<float> biasN(N, 0.f);
+    if (mode == 0) for (int i = 0; i < cout; i++) biasN[i] = bias[i];
+    else for (int p = 0; p < 4; p++) for (int i = 0; i < cout; i++) biasN[p * ocs + i] = bias[i];
+    float *d_in = 0, *d_res = 0, *d_bias = 0, *d_biasN = 0, *d_out_tc = 0, *d_out_ref = 0, *d_wT = 0, *d_tmp = 0;
+    __half *d_in8 = 0, *d_res8 = 0, *d_out8 = 0, *d_wpk = 0;
+    const size_t out_elems = mode == 0 ? (size_t)cout * hw : (size_t)cout * hw * 4;
+    cudaMalloc(&d_in, cin * hw * 4); cudaMalloc(&d_in8, cin * hw * 2 * 2); cudaMalloc(&d_bias, cout * 4); cudaMalloc(&d_biasN, N * 4);
+    cudaMalloc(&d_out_tc, out_elems * 4); cudaMalloc(&d_out_ref, out_elems * 4); cudaMalloc(&d_tmp, out_elems * 4);
+    cudaMalloc(&d_out8, (size_t)cout * hw * 2 * 2); cudaMalloc(&d_wpk, wpk.size() * 2);
+    cudaMemcpy(d_in, in, cin * hw * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_bias, bias, cout * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_biasN, biasN.data(), N * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_wpk, wpk.data(), wpk.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemset(d_out_tc, 0, out_elems * 4);
+    if (res) {
+        cudaMalloc(&d_res, cout * hw * 4); cudaMalloc(&d_res8, (size_t)cout * hw * 2 * 2);
+        cudaMemcpy(d_res, res, cout * hw * 4, cudaMemcpyHostToDevice);
+        launch_planar_to_c8(d_res, d_res8, cout, h, w, split, st);
+    }
+    launch_planar_to_c8(d_in, d_in8, cin, h, w, split, st);
+    // the reference result uses exactly the values the tensor path sees (hi+lo reconstruction of the input)
+    launch_c8_to_planar(d_in8, d_in, cin, h, w, split, st);
+    if (res) launch_c8_to_planar(d_res8, d_res, cout, h, w, split, st);
+    TcConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.wpk = d_wpk; a.bias = d_biasN; a.res = d_res8; a.res_plane = (size_t)cout * hw; a.res_split = split;
+    a.out = d_out8; a.out_plane = (size_t)cout * hw; a.out_f32 = d_out_tc; a.slope = slope;
+    a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = N; a.split_in = split; a.split_out = split;
+    a.epi = mode == 0 ? TC_EPI_C8 : TC_EPI_DECONV;
+    a.res_mode = res ? 1 : 0;
+    a.act_mode = mode == 0 ? 1 : 0;
+    a.ocs = ocs; a.ps = ps;
+    int r = launch_tc_conv(a, d_in8, st);
+    if (r) { fprintf(stderr, "launch_tc_conv failed: %d\n", r); return RIFE_B200_ERR_INTERNAL; }
+    if (mode == 0) launch_c8_to_planar(d_out8, d_out_tc, cout, h, w, split, st);
+    // fp32 CUDA-core reference
+    {
+        int ocpad = (cout + 63) / 64 * 64;
+        std::vector<float> t;
+        ConvArgs c;
+        memset(&c, 0, sizeof c);
+        if (mode == 0) {
+            t.assign((size_t)cin * 9 * ocpad, 0.f);
+            for (int oc = 0; oc < cout; oc++) for (int ic = 0; ic < cin; ic++) for (int k = 0; k < 9; k++) t[((size_t)ic * 9 + k) * ocpad + oc] = wq[((size_t)oc * cin + ic) * 9 + k];
+        } else {
+            t.assign((size_t)4 * cin * 4 * ocpad, 0.f);
+            for (int p = 0; p < 4; p++) for (int ic = 0; ic < cin; ic++) for (int rr = 0; rr < 2; rr++) for (int cc = 0; cc < 2; cc++) {
+                int ky = 3 - (p >> 1) - 2 * rr, kx = 3 - (p & 1) - 2 * cc;
+                for (int oc = 0; oc < cout; oc++) t[(((size_t)p * cin + ic) * 4 + rr * 2 + cc) * ocpad + oc] = wq[((size_t)oc * cin + ic) * 16 + ky * 4 + kx];
+            }
+        }
+        cudaMalloc(&d_wT, t.size() * 4);
+        cudaMemcpy(d_wT, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
+        c.in = d_in; c.wT = d_wT; c.bias = d_bias; c.Cin = cin; c.H = h; c.W = w; c.Cout = cout; c.ocpad = ocpad;
+        if (mode == 0) {
+            c.out = d_out_ref; c.OH = h; c.OW = w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 1; c.nparity = 1;
+            c.res = d_res; c.post_act = 2; c.post_p0 = slope;
+            launch_conv(c, 3, 1, st);
+        } else {
+            c.out = d_tmp; c.OH = 2 * h; c.OW = 2 * w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 2; c.nparity = 4;
+            launch_conv(c, 2, 1, st);
+            if (ps > 1) launch_pixelshuffle(d_tmp, cout, 2 * h, 2 * w, d_out_ref, ps, st);
+            else cudaMemcpyAsync(d_out_ref, d_tmp, out_elems * 4, cudaMemcpyDeviceToDevice, st);
+        }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fprintf(stderr, "selftest_conv: %s\n", cudaGetErrorString(e)); return RIFE_B200_ERR_DEVICE; }
+    cudaMemcpy(out_tc, d_out_tc, out_elems * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out_ref, d_out_ref, out_elems * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_res); cudaFree(d_bias); cudaFree(d_biasN); cudaFree(d_out_tc); cudaFree(d_out_ref); cudaFree(d_wT); cudaFree(d_tmp);
+    cudaFree(d_in8); cudaFree(d_res8); cudaFree(d_out8); cudaFree(d_wpk);
+    return RIFE_B200_OK;
+    GUARD_END
+}
+
+extern "C" int rife_b200_set_stream(rife_b200_t* h, void* cuda_stream) {
+    GUARD_BEGIN
+    if (!h) return RIFE_B200_ERR_ARG;
+    h->eng->set_stream((cudaStream_t)cuda_stream);
+    return RIFE_B200_OK;
+    GUARD_END
+}
+
+extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters) {
+    GUARD_BEGIN
+    using namespace rife;
+    if (cin % 16 || cout % 16 || cin <= 0 || h <= 0 || w <= 0 || iters <= 0) return RIFE_B200_ERR_ARG;
+    if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
+    struct Cache { int cin = 0, cout = 0, h = 0, w = 0, split = -1; __half *in8 = 0, *out8 = 0, *wpk = 0; float* bias = 0; };
+    static Cache c;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t hw = (size_t)h * w;
+    if (c.cin != cin || c.cout != cout || c.h != h || c.w != w || c.split != split) {
+        cudaFree(c.in8); cudaFree(c.out8); cudaFree(c.wpk); cudaFree(c.bias);
+        std::vector<float> wq((size_t)cout * cin * 9);
+        uint32_t s = 12345u;
+        for (auto& v : wq) { s = s * 1664525u + 1013904223u; v = __half2float(__float2half_rn(((s >> 9) & 1023) / 1024.f * 0.02f - 0.01f)); }
+        std::vector<uint16_t> pk;
+        pack_conv3x3_weights(wq.data(), cout, cin, cout, pk);
+        std::vector<float> x((size_t)cin * hw), b(cout, 0.01f);
+        for (auto& v : x) { s = s * 1664525u + 1013904223u; v = ((s >> 9) & 1023) / 1024.f - 0.5f; }
+        float* d_x = 0;
+        cudaMalloc(&d_x, x.size() * 4); cudaMalloc(&c.in8, x.size() * 4); cudaMalloc(&c.out8, (size_t)cout * hw * 4);
+        cudaMalloc(&c.wpk, pk.size() * 2); cudaMalloc(&c.bias, cout * 4);
+        cudaMemcpy(d_x, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(c.wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(c.bias, b.data(), cout * 4, cudaMemcpyHostToDevice);
+        launch_planar_to_c8(d_x, c.in8, cin, h, w, split, 0);
+        cudaDeviceSynchronize();
+        cudaFree(d_x);
+        c.cin = cin; c.cout = cout; c.h = h; c.w = w; c.split = split;
+    }
+    TcConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.wpk = c.wpk; a.bias = c.bias; a.out = c.out8; a.out_plane = (size_t)cout * hw; a.slope = 0.2f;
+    a.res = cin == cout ? c.in8 : nullptr; a.res_plane = (size_t)cin * hw; a.res_split = split; a.res_mode = cin == cout ? 1 : 0;
+    a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = cout; a.split_in = split; a.split_out = split; a.epi = TC_EPI_C8; a.act_mode = 1;
+    for (int i = 0; i < iters; i++) {
+        int r = launch_tc_conv(a, c.in8, st);
+        if (r) return RIFE_B200_ERR_INTERNAL;
+    }
+    return cudaGetLastError() == cudaSuccess ? RIFE_B200_OK : RIFE_B200_ERR_DEVICE;
+    GUARD_END
+}

@@ -110,6 +110,11 @@ int Engine::load_packed(const void* data, size_t bytes) {
         if (parse_net(ptxt, bbin, kNetNames[i], nets_[i], err)) { last_error = err; return -3; }
         delete run_[i];
         run_[i] = new NetRunner();
+        run_[i]->tc_mode = precision_;
+        {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, gpuid_) == cudaSuccess) run_[i]->num_sms = prop.multiProcessorCount;
+        }
         if (run_[i]->init(&nets_[i], err)) { last_error = err; return -3; }
     }
     packed_.assign(p, bytes);
@@ -119,7 +124,12 @@ int Engine::load_packed(const void* data, size_t bytes) {
 
 int Engine::set_option(const std::string& key, int value) {
     std::lock_guard<std::mutex> lk(mu_);
-    if (key == "precision") { precision_ = value; return 0; }
+    if (key == "precision") {  // 0 exact fp32, 1 tensor cores + split-fp16 activations, 2 tensor cores + plain fp16 activations
+        precision_ = value;
+        for (auto& r : run_) if (r) { r->tc_mode = value; r->clear_plans(); }
+        return 0;
+    }
+    if (key == "async") { async_ = value != 0; return 0; }
     if (key == "fuse") { for (auto& r : run_) if (r) r->fuse = value != 0; return 0; }
     last_error = "unknown option " + key;
     return -1;
@@ -159,13 +169,15 @@ int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, in
     size_t n = (size_t)w * h * 3;
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
+    cudaStream_t st = use_user_stream_ ? user_stream_ : st_;
     if (t == 0.f || t == 1.f) {
-        cudaMemcpyAsync(d_out, t == 0.f ? d_in0 : d_in1, n, cudaMemcpyDeviceToDevice, st_);
+        cudaMemcpyAsync(d_out, t == 0.f ? d_in0 : d_in1, n, cudaMemcpyDeviceToDevice, st);
     } else {
-        int r = run_device(d_in0, d_in1, w, h, t, d_out, st_);
+        int r = run_device(d_in0, d_in1, w, h, t, d_out, st);
         if (r) return r;
     }
-    cudaError_t e = cudaStreamSynchronize(st_);
+    if (async_) return 0;
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }

@@ -34,6 +34,7 @@ public:
     int process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out);
     int process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out);
     int set_option(const std::string& key, int value);
+    void set_stream(cudaStream_t s) { std::lock_guard<std::mutex> lk(mu_); user_stream_ = s; use_user_stream_ = s != nullptr; }
     std::string last_error;
 
 private:
@@ -47,6 +48,9 @@ private:
     bool tta_, ttat_, uhd_, v2_, v4_;
     bool loaded_ = false;
     int precision_ = 1;
+    bool async_ = false;
+    cudaStream_t user_stream_ = nullptr;
+    bool use_user_stream_ = false;
     Net nets_[3];           // flownet, contextnet, fusionnet
     NetRunner* run_[3] = {nullptr, nullptr, nullptr};
     std::string packed_;    // serialized model (param text + bin bytes per net)

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "tc_conv.h"
 
 namespace rife {
 
@@ -33,8 +34,15 @@ NetRunner::~NetRunner() {
         cudaFree(w.wT);
         cudaFree(w.bias);
         cudaFree(w.slope);
+        cudaFree(w.wpk);
+        cudaFree(w.biasN);
     }
     for (auto& kv : plans_) cudaFree(kv.second->arena);
+}
+
+void NetRunner::clear_plans() {
+    for (auto& kv : plans_) cudaFree(kv.second->arena);
+    plans_.clear();
 }
 
 size_t NetRunner::arena_bytes() const {
@@ -83,6 +91,32 @@ int NetRunner::init(const Net* net, std::string& err) {
             W.ocpad = ocpad;
         } else if (L.type == "InnerProduct") {
             W.wT = upload(L.weight, err);
+        }
+        // tensor-core eligibility (tc_conv.cu): 3x3 s1 p1 conv with Cin % 16 == 0 and N in {32,64,96,128,192};
+        // deconv 4x4 s2 p1 re-expressed as a 3x3 conv with N = 4 * ocs in {32, 96}
+        if ((L.type == "Convolution" || L.type == "Deconvolution") && L.weight_is_fp16) {
+            int cout = L.geti(0, 0), k = L.geti(1, 0);
+            bool isconv = L.type == "Convolution";
+            int kk = isconv ? 9 : 16;
+            int cin = (int)(L.weight.size() / ((size_t)cout * kk));
+            int N = 0, ocs = 0;
+            if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout;
+            if (!isconv) { ocs = (cout + 7) / 8 * 8; N = 4 * ocs; }
+            bool nok = isconv ? (N == 32 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
+            if (nok && cin % 16 == 0 && cin >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
+                std::vector<uint16_t> pk;
+                if (isconv) pack_conv3x3_weights(L.weight.data(), cout, cin, N, pk);
+                else pack_deconv4x4_weights(L.weight.data(), cout, cin, ocs, N, pk);
+                std::vector<float> bN(N, 0.f);
+                if (!L.bias.empty()) {
+                    if (isconv) for (int i = 0; i < cout; i++) bN[i] = L.bias[i];
+                    else for (int p = 0; p < 4; p++) for (int i = 0; i < cout; i++) bN[p * ocs + i] = L.bias[i];
+                }
+                if (cudaMalloc(&W.wpk, pk.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
+                cudaMemcpy(W.wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
+                W.biasN = upload(bN, err);
+                W.tcN = N; W.ocs = ocs; W.cin = cin;
+            }
         }
         if (!L.bias.empty()) W.bias = upload(L.bias, err);
         if (!L.slope.empty()) W.slope = upload(L.slope, err);
@@ -207,6 +241,22 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
                 }
             }
         }
+        if (tc_mode > 0 && dw_[l].wpk && plan.external_slot[L.tops[0]] < 0) {
+            int own_act = L.geti(9, 0);
+            if (L.type == "Convolution") {
+                bool ok = own_act == 0 || (own_act == 2 && s.fused_act_layer < 0 && s.fused_add_blob < 0);
+                if (ok) s.kind = 1;
+            } else if (s.fused_act_layer < 0 && (own_act == 0 || own_act == 4)) {
+                s.kind = 1;
+                int c1 = sole_consumer(L.tops[0]);
+                if (c1 >= 0 && net.layers[c1].type == "PixelShuffle" && net.layers[c1].geti(0, 1) == 2 && net.layers[c1].geti(1, 0) == 0 &&
+                    L.geti(0, 0) % 4 == 0 && plan.external_slot[net.layers[c1].tops[0]] < 0) {
+                    s.fused_ps_layer = c1;
+                    s.out_blob = net.layers[c1].tops[0];
+                    skipped[c1] = 1;
+                }
+            }
+        }
         plan.steps.push_back(s);
     }
     // 4. shape inference + alias analysis
@@ -296,38 +346,99 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             err = "unsupported layer type " + T + " (" + L.name + ")";
             return -24;
         }
+        if (s.fused_ps_layer >= 0) { o.c /= 4; o.h *= 2; o.w *= 2; }
         int ob = s.out_blob;
         plan.blobs[ob] = o;
         root[ob] = ob;
         eoff[ob] = 0;
         if (s.fused_add_blob >= 0 && !same_shape(plan.blobs[s.fused_add_blob], o)) { err = "internal: fused residual shape mismatch at " + L.name; return -22; }
     }
-    // 5. liveness + arena assignment
-    const int ns = (int)plan.steps.size();
-    std::vector<int> last_use(nb, -1);
-    for (int i = 0; i < ns; i++) {
-        const Step& s = plan.steps[i];
-        const Layer& L = net.layers[s.layer];
-        for (int b : L.bottoms)
-            if (root[b] >= 0) last_use[root[b]] = std::max(last_use[root[b]], i);
-        if (s.fused_add_blob >= 0) last_use[root[s.fused_add_blob]] = std::max(last_use[root[s.fused_add_blob]], i);
-    }
-    for (int b : plan.out_ids) last_use[root[b]] = 1 << 30;
-    plan.offset.assign(nb, (size_t)-1);
-    FreeList fl;
-    std::vector<std::vector<int>> free_at(ns);
-    for (int i = 0; i < ns; i++) {
-        const Step& s = plan.steps[i];
-        const Layer& L = net.layers[s.layer];
-        if (L.type != "Split" && L.type != "Crop") {
-            int ob = s.out_blob;
-            size_t bytes = plan.blobs[ob].count() * sizeof(float);
-            plan.offset[ob] = fl.alloc(bytes);
-            int lu = last_use[ob];
-            if (lu < i) lu = i;
-            if (lu < ns) free_at[lu].push_back(ob);
+    // 5. storage formats: a root blob may exist as planar fp32 and/or C8 fp16 (tensor-core layout); insert the
+    //    conversions a consumer needs, then do liveness + arena assignment over (root, format) storages
+    plan.split = tc_mode == 1;
+    {
+        // a tensor-core step needs whole-blob inputs (no channel-offset aliases)
+        for (Step& s : plan.steps) {
+            if (s.kind != 1) continue;
+            const Layer& L = net.layers[s.layer];
+            bool ok = eoff[L.bottoms[0]] == 0 && plan.blobs[L.bottoms[0]].dims == 3 && plan.blobs[L.bottoms[0]].c == dw_[s.layer].cin;
+            if (s.fused_add_blob >= 0 && eoff[s.fused_add_blob] != 0) ok = false;
+            if (s.fused_add_blob >= 0 && plan.blobs[root[s.fused_add_blob]].c != plan.blobs[s.fused_add_blob].c) ok = false;
+            if (plan.blobs[root[L.bottoms[0]]].c != plan.blobs[L.bottoms[0]].c) ok = false;
+            if (!ok) {
+                if (s.fused_ps_layer >= 0) { err = "internal: cannot undo pixelshuffle fusion at " + L.name; return -22; }
+                s.kind = 0;
+            }
         }
-        for (int fb : free_at[i]) fl.release(plan.offset[fb], plan.blobs[fb].count() * sizeof(float));
+        std::vector<Step> final_steps;
+        std::vector<char> have_planar(nb, 0), have_c8(nb, 0);
+        for (int b = 0; b < nb; b++)
+            if (plan.external_slot[b] >= 0) have_planar[b] = 1;
+        auto require = [&](int blob, bool c8) {
+            int r = root[blob];
+            if (c8 && !have_c8[r]) {
+                Step c; c.kind = 2; c.conv_root = r;
+                final_steps.push_back(c);
+                have_c8[r] = 1;
+            } else if (!c8 && !have_planar[r]) {
+                Step c; c.kind = 3; c.conv_root = r;
+                final_steps.push_back(c);
+                have_planar[r] = 1;
+            }
+        };
+        for (const Step& s : plan.steps) {
+            const Layer& L = net.layers[s.layer];
+            bool tc = s.kind == 1;
+            for (int b : L.bottoms) require(b, tc);
+            if (s.fused_add_blob >= 0) require(s.fused_add_blob, tc);
+            final_steps.push_back(s);
+            if (L.type == "Split" || L.type == "Crop") continue;
+            if (tc && L.type == "Convolution") have_c8[s.out_blob] = 1;
+            else have_planar[s.out_blob] = 1;
+        }
+        for (int b : plan.out_ids) require(b, false);
+        plan.steps.swap(final_steps);
+    }
+    const int ns = (int)plan.steps.size();
+    // storage id = root * 2 + (c8 ? 1 : 0)
+    std::vector<int> birth(2 * nb, -1), death(2 * nb, -1);
+    auto touch = [&](int blob, bool c8, int i, bool write) {
+        int sid = root[blob] * 2 + (c8 ? 1 : 0);
+        if (write && birth[sid] < 0) birth[sid] = i;
+        death[sid] = std::max(death[sid], i);
+    };
+    for (int i = 0; i < ns; i++) {
+        const Step& s = plan.steps[i];
+        if (s.kind == 2) { touch(s.conv_root, false, i, false); touch(s.conv_root, true, i, true); continue; }
+        if (s.kind == 3) { touch(s.conv_root, true, i, false); touch(s.conv_root, false, i, true); continue; }
+        const Layer& L = net.layers[s.layer];
+        bool tc = s.kind == 1;
+        for (int b : L.bottoms) touch(b, tc, i, false);
+        if (s.fused_add_blob >= 0) touch(s.fused_add_blob, tc, i, false);
+        if (L.type == "Split" || L.type == "Crop") continue;
+        touch(s.out_blob, tc && L.type == "Convolution", i, true);
+    }
+    for (int b : plan.out_ids) death[root[b] * 2] = 1 << 30;
+    plan.offset.assign(nb, (size_t)-1);
+    plan.offset_c8.assign(nb, (size_t)-1);
+    auto storage_bytes = [&](int sid) -> size_t {
+        const Tensor& t = plan.blobs[sid / 2];
+        return (sid & 1) ? t.count() * sizeof(uint16_t) * (plan.split ? 2 : 1) : t.count() * sizeof(float);
+    };
+    FreeList fl;
+    std::vector<std::vector<int>> born_at(ns), free_at(ns);
+    for (int sid = 0; sid < 2 * nb; sid++) {
+        if (birth[sid] < 0) continue;  // external or never materialised
+        born_at[birth[sid]].push_back(sid);
+        if (death[sid] < ns) free_at[std::max(death[sid], birth[sid])].push_back(sid);
+    }
+    for (int i = 0; i < ns; i++) {
+        for (int sid : born_at[i]) {
+            size_t off = fl.alloc(storage_bytes(sid));
+            if (sid & 1) plan.offset_c8[sid / 2] = off;
+            else plan.offset[sid / 2] = off;
+        }
+        for (int sid : free_at[i]) fl.release((sid & 1) ? plan.offset_c8[sid / 2] : plan.offset[sid / 2], storage_bytes(sid));
     }
     plan.arena_size = fl.top;
     if (plan.arena_size) CUDA_OK(cudaMalloc(&plan.arena, plan.arena_size));
@@ -357,8 +468,9 @@ int NetRunner::run(const std::vector<std::pair<std::string, Tensor>>& inputs, co
     for (size_t b = 0; b < plan.blobs.size(); b++) {
         int r = root[b];
         if (r < 0) continue;
-        float* base = plan.external_slot[r] >= 0 ? inputs[plan.external_slot[r]].second.p : (float*)((char*)plan.arena + plan.offset[r]);
-        plan.blobs[b].p = base + eoff[b];
+        float* base = plan.external_slot[r] >= 0 ? inputs[plan.external_slot[r]].second.p
+                      : (plan.offset[r] != (size_t)-1 ? (float*)((char*)plan.arena + plan.offset[r]) : nullptr);
+        plan.blobs[b].p = base ? base + eoff[b] : nullptr;
     }
     for (const Step& s : plan.steps) {
         int r = exec_step(plan, s, st, err);
@@ -371,6 +483,58 @@ int NetRunner::run(const std::vector<std::pair<std::string, Tensor>>& inputs, co
 
 int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string& err) {
     const Net& net = *net_;
+    auto c8ptr = [&](int blob) -> __half* { return (__half*)((char*)plan.arena + plan.offset_c8[plan.root[blob]]); };
+    if (s.kind == 2 || s.kind == 3) {
+        const Tensor& t = plan.blobs[s.conv_root];
+        if (s.kind == 2) launch_planar_to_c8(t.p, c8ptr(s.conv_root), t.c, t.h, t.w, plan.split, st);
+        else launch_c8_to_planar(c8ptr(s.conv_root), t.p, t.c, t.h, t.w, plan.split, st);
+        return 0;
+    }
+    if (s.kind == 1) {
+        const Layer& L = net.layers[s.layer];
+        const DeviceWeights& W = dw_[s.layer];
+        const Tensor& x = plan.blobs[L.bottoms[0]];
+        const Tensor& o = plan.blobs[s.out_blob];
+        TcConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.wpk = (const __half*)W.wpk;
+        a.bias = W.biasN;
+        a.H = x.h; a.W = x.w; a.Cin = x.c; a.Cout = L.geti(0, 0); a.N = W.tcN;
+        a.split_in = plan.split;
+        a.num_sms = num_sms;
+        if (L.type == "Convolution") {
+            a.epi = TC_EPI_C8;
+            a.out = c8ptr(s.out_blob);
+            a.out_plane = o.count();
+            a.split_out = plan.split;
+            if (s.fused_add_blob >= 0) {
+                a.res = c8ptr(s.fused_add_blob);
+                a.res_plane = plan.blobs[s.fused_add_blob].count();
+                a.res_split = plan.split;
+                a.res_mode = 1;
+            }
+            if (L.geti(9, 0) == 2) {
+                const ParamVal* ap = L.get(10);
+                a.act_mode = 1;
+                a.slope = ap && !ap->af.empty() ? ap->af[0] : 0.f;
+            }
+            if (s.fused_act_layer >= 0) {
+                const Layer& A = net.layers[s.fused_act_layer];
+                if (A.type == "ReLU") { a.act_mode = 1; a.slope = A.getf(0, 0.f); }
+                else if (A.slope.size() == 1) { a.act_mode = 1; a.slope = A.slope[0]; }
+                else { a.act_mode = 2; a.prelu = dw_[s.fused_act_layer].slope; }
+            }
+        } else {
+            a.epi = TC_EPI_DECONV;
+            a.out_f32 = o.p;
+            a.ocs = W.ocs;
+            a.ps = s.fused_ps_layer >= 0 ? 2 : 1;
+            a.act_mode = L.geti(9, 0) == 4 ? 3 : 0;
+        }
+        int r = launch_tc_conv(a, c8ptr(L.bottoms[0]), st);
+        if (r) { err = "launch_tc_conv failed for " + L.name; return -32; }
+        return 0;
+    }
     const Layer& L = net.layers[s.layer];
     const DeviceWeights& W = dw_[s.layer];
     const std::string& T = L.type;

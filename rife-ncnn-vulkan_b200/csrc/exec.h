@@ -31,6 +31,10 @@ struct DeviceWeights {
     float* bias = nullptr;
     float* slope = nullptr;
     int ocpad = 0;
+    // tensor-core path (tc_conv.cu): packed fp16 weights, bias padded to the GEMM N
+    void* wpk = nullptr;
+    float* biasN = nullptr;
+    int tcN = 0, ocs = 0, cin = 0;
 };
 
 class NetRunner {
@@ -40,6 +44,9 @@ public:
     int init(const Net* net, std::string& err);  // uploads weights to the current device
     const Net* net() const { return net_; }
     bool fuse = true;  // conv+add+leaky / conv+prelu epilogue fusion
+    int tc_mode = 1;   // 0: fp32 CUDA-core kernels only; 1: tcgen05 with split-fp16 (hi+lo) activations; 2: tcgen05, plain fp16
+    int num_sms = 148;
+    void clear_plans();
 
     // Runs the sub-graph needed for `outputs` given `inputs`.  Output tensors point into plan-owned memory that
     // stays valid until the next run() of the same (inputs-shape, outputs) signature.
@@ -50,15 +57,20 @@ public:
 
 private:
     struct Step {
-        int layer;
+        int kind = 0;              // 0 generic layer, 1 tcgen05 conv / deconv, 2 planar -> C8, 3 C8 -> planar
+        int layer = -1;
         int fused_add_blob = -1;   // residual blob id fused into the conv epilogue
         int fused_act_layer = -1;  // ReLU / PReLU layer index fused after
+        int fused_ps_layer = -1;   // PixelShuffle fused into the tensor-core deconv epilogue
         int out_blob = -1;         // blob written (differs from layer top when fused)
+        int conv_root = -1;        // kinds 2/3: root blob converted
     };
     struct Plan {
         std::vector<Step> steps;
         std::vector<Tensor> blobs;       // shape + (arena-relative) pointer per blob id
-        std::vector<size_t> offset;      // arena offset or (size_t)-1 for external
+        std::vector<size_t> offset;      // arena offset (planar fp32 storage) or (size_t)-1
+        std::vector<size_t> offset_c8;   // arena offset of the C8 fp16 storage of a root blob or (size_t)-1
+        int split = 0;                   // C8 tensors carry a lo plane
         std::vector<int> external_slot;  // blob id -> index into inputs, or -1
         float* arena = nullptr;
         size_t arena_size = 0;

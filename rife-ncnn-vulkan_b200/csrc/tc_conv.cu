@@ -1,0 +1,460 @@
+// tc_conv.cu -- 3x3 stride-1 pad-1 convolution (and deconv4x4s2 re-expressed as a 3x3 conv with 4x the output
+// channels) as an implicit GEMM on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma (fp16 operands,
+// fp32 accumulation in TMEM) -> tcgen05.ld epilogue.  sm_100a only.
+//
+// Activations live in HBM in the "C8 planar" layout  [plane][C/8][H][W][8] fp16  (plane 0 = hi, plane 1 = lo where
+// v ~= hi + lo is the split-fp16 representation of an fp32 value; SURVEY.md Appendix C: split operands reproduce the
+// fp32 oracle at its own noise floor, plain fp16 storage does not reach +-1 LSB on every layer).
+//
+// Work item = a tile of TH x 62 output pixels (TH = 2*MT rows), flattened onto MT accumulators of 128 rows x N
+// columns; the A operand of tap (dy,dx) for accumulator m is simply the shared-memory tile viewed from the
+// start address  ((2m+dy)*64 + dx) * 16 B  (no-swizzle K-major core matrices: 8 pixels x 16 B contiguous), so one
+// halo tile serves all 9 taps.  Out-of-image halo pixels are zero-filled by TMA = the convolution's zero padding.
+// Pipeline stage = 16 input channels: A_hi (+A_lo) tile slabs + the weights of all 9 taps for those channels.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "tc_conv.h"
+#include "kernels.h"
+
+namespace rife {
+
+namespace {
+
+constexpr int TWP = 64;        // tile width incl. 1-pixel halo left and right -> 62 valid output columns
+constexpr int TVALID = TWP - 2;
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 format, version field = 1):
+// core matrix = 8 rows x 16 B contiguous; SBO = byte distance between 8-row groups, LBO = between the two 16 B K halves.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct HalfPack8 {
+    uint4 v;
+};
+__device__ __forceinline__ uint32_t pack2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
+
+}  // namespace
+
+// N = UMMA N (output columns per accumulator), MT = accumulators (128 flattened positions each) per tile,
+// STAGES = pipeline depth.
+template <int N, int MT, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, TcConvArgs a) {
+    constexpr int ROWS = 2 * MT + 2;              // input rows per tile (halo included)
+    constexpr int A_PLANE = 2 * ROWS * TWP * 16;  // bytes of one plane slab: 2 eight-channel halves
+    constexpr int W_BYTES = 9 * 2 * N * 16;
+    constexpr int ACC_COLS = MT * N;              // TMEM columns per accumulator set
+    static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "invalid UMMA N");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int nplanes = a.split_in ? 2 : 1;
+    const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes + 1024);  // +1024: overrun pad for the last tap of the last slab
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = a.tiles_x * a.tiles_y;
+    const int KC = a.Cin / 16;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+                const int x0 = tx * TVALID, y0 = ty * (2 * MT);
+                for (int kc = 0; kc < KC; kc++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + W_BYTES));
+                    for (int p = 0; p < nplanes; p++)
+                        tma_load_3d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (a.Cin / 8) + 2 * kc);
+                    bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major A and B
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+                const int buf = tcount & 1;
+                const uint32_t aph = (tcount >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < KC; kc++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t wb = st + nplanes * A_PLANE;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; tap++) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint64_t bdesc = make_desc(wb + tap * (2 * N * 16), N * 16, 128);
+#pragma unroll
+                        for (int m = 0; m < MT; m++) {
+                            const uint32_t aoff = (uint32_t)(((2 * m + dy) * TWP + dx) * 16);
+                            for (int p = 0; p < nplanes; p++) {
+                                const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
+                                umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, (kc | tap | p) != 0);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t tcount = 0;
+        const size_t HW = (size_t)a.H * a.W;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const int buf = tcount & 1;
+            const uint32_t aph = (tcount >> 1) & 1;
+            const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+            const int x0 = tx * TVALID, y0 = ty * (2 * MT);
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int m = 0; m < MT; m++) {
+                const int p = q * 32 + lane;  // flattened position inside accumulator m
+                const int xr = p & (TWP - 1), yr = 2 * m + (p >> 6);
+                const int x = x0 + xr, y = y0 + yr;
+                const bool valid = xr < TVALID && x < a.W && y < a.H;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N;
+#pragma unroll 1
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(trow + c0, r);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + __ldg(a.bias + c0 + j);
+                    if (a.epi == TC_EPI_C8) {
+                        // bias (+ residual) + activation -> C8 planar fp16 (hi [+ lo])
+#pragma unroll
+                        for (int g = 0; g < 2; g++) {
+                            const int cg = (c0 >> 3) + g;  // 8-channel group
+                            if (cg * 8 >= a.Cout) break;
+                            const size_t off = ((size_t)cg * HW + (size_t)y * a.W + x) * 8;
+                            float* vv = v + g * 8;
+                            if (a.res_mode == 1) {
+                                uint4 rh = __ldg(reinterpret_cast<const uint4*>(a.res + off));
+                                const __half* h = reinterpret_cast<const __half*>(&rh);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) vv[j] += __half2float(h[j]);
+                                if (a.res_split) {
+                                    uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
+                                    const __half* l = reinterpret_cast<const __half*>(&rl);
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) vv[j] += __half2float(l[j]);
+                                }
+                            }
+                            if (a.act_mode == 1) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
+                            } else if (a.act_mode == 2) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) { float s = __ldg(a.prelu + cg * 8 + j); vv[j] = vv[j] < 0.f ? vv[j] * s : vv[j]; }
+                            }
+                            if (a.res_mode == 2) {
+                                uint4 rh = __ldg(reinterpret_cast<const uint4*>(a.res + off));
+                                const __half* h = reinterpret_cast<const __half*>(&rh);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) vv[j] += __half2float(h[j]);
+                                if (a.res_split) {
+                                    uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
+                                    const __half* l = reinterpret_cast<const __half*>(&rl);
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) vv[j] += __half2float(l[j]);
+                                }
+                            }
+                            __half hi[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) hi[j] = __float2half_rn(vv[j]);
+                            uint4 oh = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+                            *reinterpret_cast<uint4*>(a.out + off) = oh;
+                            if (a.split_out) {
+                                __half lo[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) lo[j] = __float2half_rn(vv[j] - __half2float(hi[j]));
+                                uint4 ol = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+                                *reinterpret_cast<uint4*>(a.out + a.out_plane + off) = ol;
+                            }
+                        }
+                    } else {
+                        // deconv4x4s2 (+ optional PixelShuffle r) epilogue: column n = parity * ocs + oc
+                        // deconv output pixel (2y+py, 2x+px), channel oc; PixelShuffle: oc = qq*r*r + sh*r + sw
+                        const int r = a.ps, rr = r * r;
+                        const int OH = a.H * 2 * r, OW = a.W * 2 * r;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int n = c0 + j;
+                            const int par = n / a.ocs, oc = n - par * a.ocs;
+                            if (par >= 4 || oc >= a.Cout) continue;
+                            const int py = par >> 1, px = par & 1;
+                            const int qq = oc / rr, sh = (oc - qq * rr) / r, sw = oc % r;
+                            const int oy = (2 * y + py) * r + sh, ox = (2 * x + px) * r + sw;
+                            float val = v[j];
+                            if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
+                            a.out_f32[((size_t)qq * OH + oy) * OW + ox] = val;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+template <int N, int MT, int STAGES>
+static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+    constexpr int ROWS = 2 * MT + 2;
+    constexpr int A_PLANE = 2 * ROWS * TWP * 16;
+    constexpr int W_BYTES = 9 * 2 * N * 16;
+    const int nplanes = a.split_in ? 2 : 1;
+    const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
+    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256;
+    if (smem > 227 * 1024) return -2;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+        configured = smem;
+    }
+    int ntiles = a.tiles_x * a.tiles_y;
+    int grid = ntiles < a.num_sms ? ntiles : a.num_sms;
+    tc_conv3x3_kernel<N, MT, STAGES><<<grid, NTHREADS, smem, st>>>(tm, a);
+    g_launch_count++;
+    return 0;
+}
+
+int tc_conv_tile_rows(int N) { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }
+
+int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    if (a.Cin % 16 || a.N % 16 || a.N < 16 || a.N > 256) return -4;
+    const int nplanes = a.split_in ? 2 : 1;
+    const int MT = tc_conv_tile_rows(a.N) / 2;
+    a.tiles_x = (a.W + TVALID - 1) / TVALID;
+    a.tiles_y = (a.H + 2 * MT - 1) / (2 * MT);
+    if (!a.num_sms) a.num_sms = 148;
+    // activation tensor viewed as [planes * C/8][H][W*4] 32-bit words (16 B = one pixel's 8 channels)
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * (a.Cin / 8)};
+    cuuint64_t strides[2] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16};
+    cuuint32_t box[3] = {(cuuint32_t)TWP * 4, (cuuint32_t)(2 * MT + 2), 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -5;
+    switch (a.N) {
+        case 32: return launch_t<32, 4, 4>(a, tm, st);
+        case 64: return launch_t<64, 4, 3>(a, tm, st);
+        case 96: return launch_t<96, 2, 3>(a, tm, st);
+        case 128: return launch_t<128, 2, 3>(a, tm, st);
+        case 192: return launch_t<192, 1, 3>(a, tm, st);
+        default: return -6;
+    }
+}
+
+// ---- layout conversion kernels -------------------------------------------------------------------
+// planar fp32 [C][H][W] -> C8 planar fp16 hi (+lo)
+__global__ void planar_to_c8_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H, int W, int split, size_t plane) {
+    size_t HW = (size_t)H * W;
+    size_t n = (size_t)(C / 8) * HW;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t cg = i / HW, pix = i - cg * HW;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float v = in[(cg * 8 + j) * HW + pix];
+        hi[j] = __float2half_rn(v);
+        lo[j] = __float2half_rn(v - __half2float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+    if (split) *reinterpret_cast<uint4*>(out + plane + i * 8) = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+}
+void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st) {
+    size_t n = (size_t)(C / 8) * H * W;
+    planar_to_c8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, H, W, split, (size_t)C * H * W);
+    g_launch_count++;
+}
+__global__ void c8_to_planar_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int H, int W, int split, size_t plane) {
+    size_t HW = (size_t)H * W;
+    size_t n = (size_t)(C / 8) * HW;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t cg = i / HW, pix = i - cg * HW;
+    uint4 h = *reinterpret_cast<const uint4*>(in + i * 8);
+    uint4 l = split ? *reinterpret_cast<const uint4*>(in + plane + i * 8) : make_uint4(0, 0, 0, 0);
+    const __half* hh = reinterpret_cast<const __half*>(&h);
+    const __half* ll = reinterpret_cast<const __half*>(&l);
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[(cg * 8 + j) * HW + pix] = __half2float(hh[j]) + __half2float(ll[j]);
+}
+void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st) {
+    size_t n = (size_t)(C / 8) * H * W;
+    c8_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, H, W, split, (size_t)C * H * W);
+    g_launch_count++;
+}
+
+// ---- weight packing (host) -----------------------------------------------------------------------
+// conv: w[oc][ic][3][3] fp32 (fp16-exact) -> wpk[kc][tap][half][n][8] fp16, n = oc (zero padded to N)
+void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out) {
+    out.assign((size_t)(cin / 16) * 9 * 2 * N * 8, 0);
+    for (int kc = 0; kc < cin / 16; kc++)
+        for (int tap = 0; tap < 9; tap++)
+            for (int hf = 0; hf < 2; hf++)
+                for (int n = 0; n < cout; n++)
+                    for (int j = 0; j < 8; j++) {
+                        int ic = kc * 16 + hf * 8 + j;
+                        __half h = __float2half_rn(w[((size_t)n * cin + ic) * 9 + tap]);
+                        out[((((size_t)kc * 9 + tap) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
+                    }
+}
+// deconv 4x4 s2 p1: w[oc][ic][4][4] -> 3x3-neighbourhood GEMM with n = parity*ocs + oc:
+// out(2y+py, 2x+px) = sum_{dy,dx} in(y-1+dy, x-1+dx) * w[oc][ic][3+py-2dy][3+px-2dx]  for dy-py, dx-px in {0,1}
+void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out) {
+    out.assign((size_t)(cin / 16) * 9 * 2 * N * 8, 0);
+    for (int kc = 0; kc < cin / 16; kc++)
+        for (int dy = 0; dy < 3; dy++)
+            for (int dx = 0; dx < 3; dx++)
+                for (int par = 0; par < 4; par++) {
+                    int py = par >> 1, px = par & 1;
+                    if (dy - py < 0 || dy - py > 1 || dx - px < 0 || dx - px > 1) continue;
+                    int ky = 3 + py - 2 * dy, kx = 3 + px - 2 * dx;
+                    for (int hf = 0; hf < 2; hf++)
+                        for (int oc = 0; oc < cout; oc++)
+                            for (int j = 0; j < 8; j++) {
+                                int ic = kc * 16 + hf * 8 + j;
+                                __half h = __float2half_rn(w[((size_t)oc * cin + ic) * 16 + ky * 4 + kx]);
+                                out[((((size_t)kc * 9 + dy * 3 + dx) * 2 + hf) * N + par * ocs + oc) * 8 + j] = __half_as_ushort(h);
+                            }
+                }
+}
+
+}  // namespace rife

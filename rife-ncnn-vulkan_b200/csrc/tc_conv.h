@@ -1,0 +1,42 @@
+// tc_conv.h -- host interface of the tcgen05 implicit-GEMM convolution (tc_conv.cu)
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace rife {
+
+enum { TC_EPI_C8 = 0, TC_EPI_DECONV = 1 };
+
+struct TcConvArgs {
+    const __half* wpk;      // packed weights [Cin/16][9][2][N][8]
+    const float* bias;      // [N] (zero padded)
+    const __half* res;      // residual in C8 layout (Cout channels) or null
+    size_t res_plane;       // element offset of the residual's lo plane
+    __half* out;            // C8 output (TC_EPI_C8)
+    size_t out_plane;       // element offset of the output's lo plane
+    float* out_f32;         // planar fp32 output (TC_EPI_DECONV)
+    const float* prelu;     // per-channel slopes (act_mode 2)
+    float slope;            // leaky slope (act_mode 1)
+    int H, W, Cin, Cout, N; // N = GEMM columns (Cout for conv, 4*ocs for deconv)
+    int split_in, split_out, res_split;
+    int epi;                // TC_EPI_*
+    int res_mode;           // 0 none, 1 add before activation, 2 add after activation
+    int act_mode;           // 0 none, 1 leaky(slope), 2 prelu, 3 sigmoid (deconv epilogue only)
+    int ocs, ps;            // deconv: output-channel slots per parity, PixelShuffle factor (1 = none)
+    int tiles_x, tiles_y, num_sms;  // filled by the launcher
+};
+
+// `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
+int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st);
+int tc_conv_tile_rows(int N);
+
+void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st);
+void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st);
+
+void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out);
+void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out);
+
+}  // namespace rife

@@ -90,8 +90,8 @@ def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd
             cmd.append("--tta-temporal")
         if uhd:
             cmd.append("--uhd")
-        if threads:
-            cmd += ["--threads", str(threads)]
+        # small frames on a many-core host: cap the OpenMP team (128 threads on a 96x64 image crawl)
+        cmd += ["--threads", str(threads or min(os.cpu_count() or 1, 16))]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle failed: %s\n%s" % (" ".join(cmd), r.stderr[-2000:]))

@@ -1,0 +1,58 @@
+"""tcgen05 implicit-GEMM convolution vs the fp32 CUDA-core kernel on the same seeded data (per layer).
+Operands are fp16-exact weights and split-fp16 (hi+lo) or plain fp16 activations; the reference result is computed
+in fp32 from exactly the values the tensor path sees, so the tolerance only covers fp32 accumulation order and the
+output rounding (split: ~2^-22 relative; plain fp16 output: 2^-11 relative)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(cin, cout, h, w, kk, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((cin, h, w), dtype=np.float32)
+    wgt = (rng.standard_normal((cout, cin, kk), dtype=np.float32) / np.sqrt(cin * 9)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32) * 0.1
+    res = rng.standard_normal((cout, h, w), dtype=np.float32)
+    return x, wgt, b, res
+
+
+def _check(o_tc, o_ref, split):
+    err = np.abs(o_tc - o_ref)
+    scale = np.abs(o_ref).max() + 1e-6
+    tol = (2e-5 if split else 2e-3) * scale
+    bad = np.argwhere(err > tol)
+    return float(err.max()), float(tol), bad
+
+
+@pytest.mark.parametrize("c", [64, 96, 128, 192])
+@pytest.mark.parametrize("split", [1, 0])
+def test_conv3x3_res_leaky(pkg, c, split):
+    h, w = 21, 70  # 2 column tiles (62 + 8) and a ragged last row tile
+    x, wgt, b, res = _data(c, c, h, w, 9, seed=c)
+    o_tc, o_ref = pkg.selftest_conv(0, x, wgt, b, res=res, slope=0.2, split=bool(split))
+    mx, tol, bad = _check(o_tc, o_ref, split)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
+def test_conv3x3_single_taps(pkg):
+    """One non-zero tap at a time: localises a wrong shared-memory view (row/column shift) to its (dy,dx)."""
+    c, h, w = 64, 10, 64
+    x, wgt, b, _ = _data(c, c, h, w, 9, seed=7)
+    report = []
+    for tap in range(9):
+        wt = np.zeros_like(wgt)
+        wt[:, :, tap] = wgt[:, :, tap]
+        o_tc, o_ref = pkg.selftest_conv(0, x, wt, b * 0, res=None, slope=1.0, split=True)
+        mx, tol, bad = _check(o_tc, o_ref, 1)
+        report.append((tap, mx, len(bad)))
+    assert all(n == 0 for _, _, n in report), report
+
+
+@pytest.mark.parametrize("cin,cout,ps", [(64, 24, 2), (192, 24, 2), (96, 5, 1)])
+def test_deconv_pixelshuffle(pkg, cin, cout, ps):
+    h, w = 9, 70
+    x, wgt, b, _ = _data(cin, cout, h, w, 16, seed=cin + cout)
+    o_tc, o_ref = pkg.selftest_conv(1, x, wgt, b, split=True, ps=ps)
+    mx, tol, bad = _check(o_tc, o_ref, 1)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
