@@ -168,6 +168,8 @@ def selftest_conv(mode, x, weight, bias, res=None, slope=0.2, split=True, ps=2, 
     cout = weight.shape[0]
     if mode == 0:
         oshape = (cout, h, w)
+    elif mode == 2:
+        oshape = (cout, h // 2, w // 2)
     else:
         oshape = (cout // (ps * ps), 2 * h * ps, 2 * w * ps)
     o1 = np.zeros(oshape, np.float32)

@@ -141,11 +141,60 @@ void rife_b200_destroy(rife_b200_t* h) {
 
 #include "tc_conv.h"
 
+// mode 2: conv3x3 stride 2 pad 1 (+bias +leaky): in [cin][h][w] (h, w even) -> out [cout][h/2][w/2]
+static int selftest_conv_s2(int gpuid, int cin, int cout, int h, int w, int split, const float* in, const float* weight, const float* bias, float slope,
+                            float* out_tc, float* out_ref) {
+    using namespace rife;
+    if ((h | w) & 1 || cout % 16) return RIFE_B200_ERR_ARG;
+    if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
+    cudaStream_t st = 0;
+    const int oh = h / 2, ow = w / 2, cinp = (cin + 15) / 16 * 16;
+    const size_t hw = (size_t)h * w, ohw = (size_t)oh * ow;
+    std::vector<float> wq((size_t)cout * cin * 9);
+    for (size_t i = 0; i < wq.size(); i++) wq[i] = __half2float(__float2half_rn(weight[i]));
+    std::vector<uint16_t> wpk;
+    pack_conv3x3s2_weights(wq.data(), cout, cin, cinp, cout, wpk);
+    int ocpad = (cout + 63) / 64 * 64;
+    std::vector<float> t((size_t)cin * 9 * ocpad, 0.f);
+    for (int oc = 0; oc < cout; oc++) for (int ic = 0; ic < cin; ic++) for (int k = 0; k < 9; k++) t[((size_t)ic * 9 + k) * ocpad + oc] = wq[((size_t)oc * cin + ic) * 9 + k];
+    float *d_in = 0, *d_bias = 0, *d_out_tc = 0, *d_out_ref = 0, *d_wT = 0;
+    __half *d_in8 = 0, *d_out8 = 0, *d_wpk = 0;
+    cudaMalloc(&d_in, cin * hw * 4); cudaMalloc(&d_in8, (size_t)cinp * hw * 4); cudaMalloc(&d_bias, cout * 4);
+    cudaMalloc(&d_out_tc, cout * ohw * 4); cudaMalloc(&d_out_ref, cout * ohw * 4); cudaMalloc(&d_out8, cout * ohw * 4);
+    cudaMalloc(&d_wpk, wpk.size() * 2); cudaMalloc(&d_wT, t.size() * 4);
+    cudaMemcpy(d_in, in, cin * hw * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_bias, bias, cout * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_wpk, wpk.data(), wpk.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_wT, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
+    launch_planar_to_c8(d_in, d_in8, cin, h, w, split, st, cinp, 1);
+    launch_c8_to_planar(d_in8, d_in, cin, h, w, split, st, cinp, 1);  // reference sees the same (rounded) operand values
+    TcConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.wpk = d_wpk; a.bias = d_bias; a.out = d_out8; a.out_plane = (size_t)cout * ohw; a.slope = slope;
+    a.H = oh; a.W = ow; a.Cin = cinp; a.Cout = cout; a.N = cout; a.split_in = split; a.split_out = split; a.epi = TC_EPI_C8; a.act_mode = 1; a.s2 = 1;
+    int r = launch_tc_conv(a, d_in8, st);
+    if (r) { fprintf(stderr, "launch_tc_conv(s2) failed: %d\n", r); return RIFE_B200_ERR_INTERNAL; }
+    launch_c8_to_planar(d_out8, d_out_tc, cout, oh, ow, split, st);
+    ConvArgs c;
+    memset(&c, 0, sizeof c);
+    c.in = d_in; c.wT = d_wT; c.bias = d_bias; c.out = d_out_ref; c.Cin = cin; c.H = h; c.W = w; c.Cout = cout; c.ocpad = ocpad;
+    c.OH = oh; c.OW = ow; c.DH = oh; c.DW = ow; c.in_off_y = c.in_off_x = -1; c.out_mul = 1; c.nparity = 1; c.act = 2; c.act_p0 = slope;
+    launch_conv(c, 3, 2, st);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fprintf(stderr, "selftest_conv_s2: %s\n", cudaGetErrorString(e)); return RIFE_B200_ERR_DEVICE; }
+    cudaMemcpy(out_tc, d_out_tc, cout * ohw * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out_ref, d_out_ref, cout * ohw * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_bias); cudaFree(d_out_tc); cudaFree(d_out_ref); cudaFree(d_wT); cudaFree(d_in8); cudaFree(d_out8); cudaFree(d_wpk);
+    return RIFE_B200_OK;
+}
+
 extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w, int split, int ps, const float* in, const float* weight,
                                        const float* bias, const float* res, float slope, float* out_tc, float* out_ref) {
     GUARD_BEGIN
     using namespace rife;
-    if (!in || !weight || !bias || !out_tc || !out_ref || cin % 16 || cin <= 0 || cout <= 0 || h <= 0 || w <= 0) return RIFE_B200_ERR_ARG;
+    if (!in || !weight || !bias || !out_tc || !out_ref || cin <= 0 || cout <= 0 || h <= 0 || w <= 0) return RIFE_B200_ERR_ARG;
+    if (mode != 2 && cin % 16) return RIFE_B200_ERR_ARG;
+    if (mode == 2) return selftest_conv_s2(gpuid, cin, cout, h, w, split, in, weight, bias, slope, out_tc, out_ref);
     if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
     cudaStream_t st = 0;
     const size_t hw = (size_t)h * w;

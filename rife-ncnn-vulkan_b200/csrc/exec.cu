@@ -99,13 +99,15 @@ int NetRunner::init(const Net* net, std::string& err) {
             bool isconv = L.type == "Convolution";
             int kk = isconv ? 9 : 16;
             int cin = (int)(L.weight.size() / ((size_t)cout * kk));
-            int N = 0, ocs = 0;
+            int N = 0, ocs = 0, s2 = 0, cinp = cin;
             if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout;
+            if (isconv && k == 3 && L.geti(3, 1) == 2 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) { N = cout; s2 = 1; if (cin < 16) cinp = 16; }
             if (!isconv) { ocs = (cout + 7) / 8 * 8; N = 4 * ocs; }
-            bool nok = isconv ? (N == 32 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
-            if (nok && cin % 16 == 0 && cin >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
+            bool nok = isconv ? (N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
+            if (nok && cinp % 16 == 0 && cinp >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
                 std::vector<uint16_t> pk;
-                if (isconv) pack_conv3x3_weights(L.weight.data(), cout, cin, N, pk);
+                if (isconv && s2) pack_conv3x3s2_weights(L.weight.data(), cout, cin, cinp, N, pk);
+                else if (isconv) pack_conv3x3_weights(L.weight.data(), cout, cin, N, pk);
                 else pack_deconv4x4_weights(L.weight.data(), cout, cin, ocs, N, pk);
                 std::vector<float> bN(N, 0.f);
                 if (!L.bias.empty()) {
@@ -115,7 +117,7 @@ int NetRunner::init(const Net* net, std::string& err) {
                 if (cudaMalloc(&W.wpk, pk.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
                 cudaMemcpy(W.wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
                 W.biasN = upload(bN, err);
-                W.tcN = N; W.ocs = ocs; W.cin = cin;
+                W.tcN = N; W.ocs = ocs; W.cin = cin; W.cinp = cinp; W.tc_s2 = s2;
             }
         }
         if (!L.bias.empty()) W.bias = upload(L.bias, err);
@@ -357,19 +359,38 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
     //    conversions a consumer needs, then do liveness + arena assignment over (root, format) storages
     plan.split = tc_mode == 1;
     {
-        // a tensor-core step needs whole-blob inputs (no channel-offset aliases)
+        // a tensor-core step needs whole-blob inputs (no channel-offset aliases); a stride-2 step needs even input
+        // dims and is the only tensor-core consumer format of its input (space-to-depth C8)
+        plan.c8_s2d.assign(nb, 0);
+        std::vector<char> c8_used_s1(nb, 0);
         for (Step& s : plan.steps) {
             if (s.kind != 1) continue;
             const Layer& L = net.layers[s.layer];
-            bool ok = eoff[L.bottoms[0]] == 0 && plan.blobs[L.bottoms[0]].dims == 3 && plan.blobs[L.bottoms[0]].c == dw_[s.layer].cin;
+            const DeviceWeights& W = dw_[s.layer];
+            const Tensor& x = plan.blobs[L.bottoms[0]];
+            bool ok = eoff[L.bottoms[0]] == 0 && x.dims == 3 && x.c == W.cin;
             if (s.fused_add_blob >= 0 && eoff[s.fused_add_blob] != 0) ok = false;
             if (s.fused_add_blob >= 0 && plan.blobs[root[s.fused_add_blob]].c != plan.blobs[s.fused_add_blob].c) ok = false;
-            if (plan.blobs[root[L.bottoms[0]]].c != plan.blobs[L.bottoms[0]].c) ok = false;
+            if (plan.blobs[root[L.bottoms[0]]].c != x.c) ok = false;
+            if (W.tc_s2 && ((x.h | x.w) & 1)) ok = false;
+            if (W.cinp != W.cin && tc_mode != 1) ok = false;  // narrow block-head inputs carry flow: split precision only
+            int r = root[L.bottoms[0]];
+            if (ok && W.tc_s2 && c8_used_s1[r]) ok = false;
+            if (ok && !W.tc_s2 && plan.c8_s2d[r]) ok = false;
             if (!ok) {
                 if (s.fused_ps_layer >= 0) { err = "internal: cannot undo pixelshuffle fusion at " + L.name; return -22; }
                 s.kind = 0;
+                continue;
             }
+            if (W.tc_s2) plan.c8_s2d[r] = 1; else c8_used_s1[r] = 1;
+            if (s.fused_add_blob >= 0) c8_used_s1[root[s.fused_add_blob]] = 1;
         }
+        // a residual must be in plain C8 form: demote stride-2 consumers whose input doubles as a residual
+        for (Step& s : plan.steps)
+            if (s.kind == 1 && dw_[s.layer].tc_s2 && c8_used_s1[root[net.layers[s.layer].bottoms[0]]]) {
+                plan.c8_s2d[root[net.layers[s.layer].bottoms[0]]] = 0;
+                s.kind = 0;
+            }
         std::vector<Step> final_steps;
         std::vector<char> have_planar(nb, 0), have_c8(nb, 0);
         for (int b = 0; b < nb; b++)
@@ -389,6 +410,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
         for (const Step& s : plan.steps) {
             const Layer& L = net.layers[s.layer];
             bool tc = s.kind == 1;
+            if (L.type == "Split" || L.type == "Crop") { final_steps.push_back(s); continue; }  // aliases: no data touched
             for (int b : L.bottoms) require(b, tc);
             if (s.fused_add_blob >= 0) require(s.fused_add_blob, tc);
             final_steps.push_back(s);
@@ -413,9 +435,9 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
         if (s.kind == 3) { touch(s.conv_root, true, i, false); touch(s.conv_root, false, i, true); continue; }
         const Layer& L = net.layers[s.layer];
         bool tc = s.kind == 1;
+        if (L.type == "Split" || L.type == "Crop") continue;
         for (int b : L.bottoms) touch(b, tc, i, false);
         if (s.fused_add_blob >= 0) touch(s.fused_add_blob, tc, i, false);
-        if (L.type == "Split" || L.type == "Crop") continue;
         touch(s.out_blob, tc && L.type == "Convolution", i, true);
     }
     for (int b : plan.out_ids) death[root[b] * 2] = 1 << 30;
@@ -423,7 +445,8 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
     plan.offset_c8.assign(nb, (size_t)-1);
     auto storage_bytes = [&](int sid) -> size_t {
         const Tensor& t = plan.blobs[sid / 2];
-        return (sid & 1) ? t.count() * sizeof(uint16_t) * (plan.split ? 2 : 1) : t.count() * sizeof(float);
+        const size_t cpad = (size_t)((t.c + 15) / 16 * 16);
+        return (sid & 1) ? cpad * t.h * t.w * sizeof(uint16_t) * (plan.split ? 2 : 1) : t.count() * sizeof(float);
     };
     FreeList fl;
     std::vector<std::vector<int>> born_at(ns), free_at(ns);
@@ -486,8 +509,9 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
     auto c8ptr = [&](int blob) -> __half* { return (__half*)((char*)plan.arena + plan.offset_c8[plan.root[blob]]); };
     if (s.kind == 2 || s.kind == 3) {
         const Tensor& t = plan.blobs[s.conv_root];
-        if (s.kind == 2) launch_planar_to_c8(t.p, c8ptr(s.conv_root), t.c, t.h, t.w, plan.split, st);
-        else launch_c8_to_planar(c8ptr(s.conv_root), t.p, t.c, t.h, t.w, plan.split, st);
+        const int cpad = (t.c + 15) / 16 * 16;
+        if (s.kind == 2) launch_planar_to_c8(t.p, c8ptr(s.conv_root), t.c, t.h, t.w, plan.split, st, cpad, plan.c8_s2d[s.conv_root]);
+        else launch_c8_to_planar(c8ptr(s.conv_root), t.p, t.c, t.h, t.w, plan.split, st, cpad, plan.c8_s2d[s.conv_root]);
         return 0;
     }
     if (s.kind == 1) {
@@ -499,13 +523,16 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
         memset(&a, 0, sizeof a);
         a.wpk = (const __half*)W.wpk;
         a.bias = W.biasN;
-        a.H = x.h; a.W = x.w; a.Cin = x.c; a.Cout = L.geti(0, 0); a.N = W.tcN;
+        a.H = o.h; a.W = o.w; a.Cin = W.cinp; a.Cout = L.geti(0, 0); a.N = W.tcN;
+        a.s2 = W.tc_s2;
+        if (L.type == "Deconvolution") { a.H = x.h; a.W = x.w; }
         a.split_in = plan.split;
         a.num_sms = num_sms;
         if (L.type == "Convolution") {
             a.epi = TC_EPI_C8;
             a.out = c8ptr(s.out_blob);
             a.out_plane = o.count();
+            a.out_s2d = plan.c8_s2d[plan.root[s.out_blob]];
             a.split_out = plan.split;
             if (s.fused_add_blob >= 0) {
                 a.res = c8ptr(s.fused_add_blob);

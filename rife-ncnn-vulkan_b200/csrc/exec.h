@@ -34,7 +34,7 @@ struct DeviceWeights {
     // tensor-core path (tc_conv.cu): packed fp16 weights, bias padded to the GEMM N
     void* wpk = nullptr;
     float* biasN = nullptr;
-    int tcN = 0, ocs = 0, cin = 0;
+    int tcN = 0, ocs = 0, cin = 0, cinp = 0, tc_s2 = 0;
 };
 
 class NetRunner {
@@ -71,6 +71,7 @@ private:
         std::vector<size_t> offset;      // arena offset (planar fp32 storage) or (size_t)-1
         std::vector<size_t> offset_c8;   // arena offset of the C8 fp16 storage of a root blob or (size_t)-1
         int split = 0;                   // C8 tensors carry a lo plane
+        std::vector<char> c8_s2d;        // root blob's C8 storage is in space-to-depth form (feeds a stride-2 tensor-core conv)
         std::vector<int> external_slot;  // blob id -> index into inputs, or -1
         float* arena = nullptr;
         size_t arena_size = 0;

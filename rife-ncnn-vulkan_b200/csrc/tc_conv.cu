@@ -113,11 +113,15 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) { return (uint32_t
 
 // N = UMMA N (output columns per accumulator), MT = accumulators (128 flattened positions each) per tile,
 // STAGES = pipeline depth.
-template <int N, int MT, int STAGES>
+// TAPS = 9: stride-1 conv (every K chunk uses the 9 shifted views).  TAPS = 4: stride-2 conv over a space-to-depth
+// input (4 parity sub-images [py][px] of H/2 x W/2, each a run of K chunks): input row 2y+dy-1 is row y-1 of the odd
+// sub-image for dy = 0, row y of the even one for dy = 1 and row y of the odd one for dy = 2 (columns alike), so a
+// chunk of parity (py,px) contributes (py?2:1)*(px?2:1) taps, each again a plain shifted view of the same slab.
+template <int N, int MT, int STAGES, int TAPS>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, TcConvArgs a) {
     constexpr int ROWS = 2 * MT + 2;              // input rows per tile (halo included)
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;  // bytes of one plane slab: 2 eight-channel halves
-    constexpr int W_BYTES = 9 * 2 * N * 16;
+    constexpr int W_BYTES = TAPS * 2 * N * 16;
     constexpr int ACC_COLS = MT * N;              // TMEM columns per accumulator set
     static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "invalid UMMA N");
@@ -130,10 +134,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+    float* slope_s = bias_s + N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = a.tiles_x * a.tiles_y;
-    const int KC = a.Cin / 16;
+    const int KCP = a.Cin / 16;                    // K chunks per parity sub-image (all of them for stride 1)
+    const int KC = TAPS == 9 ? KCP : 4 * KCP;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -144,6 +151,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < N; i += NTHREADS) {
+        bias_s[i] = a.bias[i];
+        slope_s[i] = (a.act_mode == 2 && i < a.Cout) ? a.prelu[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + W_BYTES));
                     for (int p = 0; p < nplanes; p++)
-                        tma_load_3d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (a.Cin / 8) + 2 * kc);
+                        tma_load_3d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc);
                     bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                 }
             }
@@ -186,18 +197,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t wb = st + nplanes * A_PLANE;
+                    if constexpr (TAPS == 9) {
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; tap++) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint64_t bdesc = make_desc(wb + tap * (2 * N * 16), N * 16, 128);
+                        for (int tap = 0; tap < 9; tap++) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint64_t bdesc = make_desc(wb + tap * (2 * N * 16), N * 16, 128);
 #pragma unroll
-                        for (int m = 0; m < MT; m++) {
-                            const uint32_t aoff = (uint32_t)(((2 * m + dy) * TWP + dx) * 16);
-                            for (int p = 0; p < nplanes; p++) {
-                                const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
-                                umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, (kc | tap | p) != 0);
+                            for (int m = 0; m < MT; m++) {
+                                const uint32_t aoff = (uint32_t)(((2 * m + dy) * TWP + dx) * 16);
+                                for (int p = 0; p < nplanes; p++) {
+                                    const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
+                                    umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, (kc | tap | p) != 0);
+                                }
                             }
                         }
+                    } else {
+                        const int par = kc / KCP, py = par >> 1, px = par & 1;
+                        const int nty = py ? 2 : 1, ntx = px ? 2 : 1;
+                        int first = kc == 0;
+#pragma unroll 1
+                        for (int iy = 0; iy < nty; iy++)
+#pragma unroll 1
+                            for (int ix = 0; ix < ntx; ix++) {
+                                // odd sub-image: slot 0 = tap d=0 (previous row/col, view offset 0), slot 1 = tap d=2 (view offset 1)
+                                // even sub-image: single slot = tap d=1 (view offset 1)
+                                const int oy = py ? iy : 1, ox = px ? ix : 1;
+                                const uint64_t bdesc = make_desc(wb + (iy * 2 + ix) * (2 * N * 16), N * 16, 128);
+#pragma unroll
+                                for (int m = 0; m < MT; m++) {
+                                    const uint32_t aoff = (uint32_t)(((2 * m + oy) * TWP + ox) * 16);
+                                    for (int p = 0; p < nplanes; p++) {
+                                        const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
+                                        umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, !(first && p == 0));
+                                    }
+                                }
+                                first = 0;
+                            }
                     }
                     umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
                 }
@@ -206,7 +241,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         }
     } else {
         // ===== epilogue warps =====
+        // Per tile the accumulators are drained in NBLK blocks of CB channels.  The residual (16 B per 8-channel group
+        // and plane) for block b+1 is fetched into registers while block b is converted and stored, and the fetch for
+        // the first block is issued before waiting for the MMAs, so global-memory latency overlaps the tensor work.
+        constexpr int CB = (N % 64 == 0) ? 64 : ((N % 48 == 0) ? 48 : 32);
+        constexpr int NCB = N / CB, NBLK = MT * NCB, G = CB / 8;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int p = q * 32 + lane;  // flattened position inside an accumulator
+        const int xr = p & (TWP - 1), yrow = p >> 6;
         uint32_t tcount = 0;
         const size_t HW = (size_t)a.H * a.W;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
@@ -214,95 +256,151 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             const uint32_t aph = (tcount >> 1) & 1;
             const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
             const int x0 = tx * TVALID, y0 = ty * (2 * MT);
-            mbar_wait(&acc_full[buf], aph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int m = 0; m < MT; m++) {
-                const int p = q * 32 + lane;  // flattened position inside accumulator m
-                const int xr = p & (TWP - 1), yr = 2 * m + (p >> 6);
-                const int x = x0 + xr, y = y0 + yr;
-                const bool valid = xr < TVALID && x < a.W && y < a.H;
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N;
-#pragma unroll 1
-                for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(trow + c0, r);
-                    tmem_ld_wait();
-                    if (!valid) continue;
-                    float v[16];
+            const int x = x0 + xr;
+            const bool xvalid = xr < TVALID && x < a.W;
+            if (a.epi == TC_EPI_C8) {
+                uint4 rb[2][2 * G];
+                auto prefetch = [&](int blk, uint4* dst) {
+                    const int m = blk / NCB, cb = blk % NCB;
+                    const int y = y0 + 2 * m + yrow;
+                    if (a.res_mode == 0 || !xvalid || y >= a.H) return;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + __ldg(a.bias + c0 + j);
-                    if (a.epi == TC_EPI_C8) {
-                        // bias (+ residual) + activation -> C8 planar fp16 (hi [+ lo])
+                    for (int g = 0; g < G; g++) {
+                        const size_t off = ((size_t)(cb * G + g) * HW + (size_t)y * a.W + x) * 8;
+                        dst[g] = __ldg(reinterpret_cast<const uint4*>(a.res + off));
+                        if (a.res_split) dst[G + g] = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
+                    }
+                };
+                prefetch(0, rb[0]);
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
 #pragma unroll
-                        for (int g = 0; g < 2; g++) {
-                            const int cg = (c0 >> 3) + g;  // 8-channel group
-                            if (cg * 8 >= a.Cout) break;
-                            const size_t off = ((size_t)cg * HW + (size_t)y * a.W + x) * 8;
-                            float* vv = v + g * 8;
-                            if (a.res_mode == 1) {
-                                uint4 rh = __ldg(reinterpret_cast<const uint4*>(a.res + off));
-                                const __half* h = reinterpret_cast<const __half*>(&rh);
+                for (int blk = 0; blk < NBLK; blk++) {
+                    if (blk + 1 < NBLK) prefetch(blk + 1, rb[(blk + 1) & 1]);
+                    const uint4* rcur = rb[blk & 1];
+                    const int m = blk / NCB, cb = blk % NCB;
+                    const int y = y0 + 2 * m + yrow;
+                    const bool valid = xvalid && y < a.H;
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N + cb * CB;
 #pragma unroll
-                                for (int j = 0; j < 8; j++) vv[j] += __half2float(h[j]);
-                                if (a.res_split) {
-                                    uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
-                                    const __half* l = reinterpret_cast<const __half*>(&rl);
+                    for (int c = 0; c < CB / 16; c++) {
+                        uint32_t r[16];
+                        tmem_ld16(trow + c * 16, r);
+                        tmem_ld_wait();
+                        if (valid) {
 #pragma unroll
-                                    for (int j = 0; j < 8; j++) vv[j] += __half2float(l[j]);
+                            for (int g2 = 0; g2 < 2; g2++) {
+                                const int gl = c * 2 + g2;           // group inside the block
+                                const int cg = cb * G + gl;          // global 8-channel group
+                                const size_t off = ((size_t)cg * HW + (size_t)y * a.W + x) * 8;
+                                // space-to-depth output (feeds a stride-2 tensor-core conv): [py*2+px][C/8][H/2][W/2][8]
+                                const size_t ooff = !a.out_s2d ? off
+                                    : ((((size_t)((y & 1) * 2 + (x & 1)) * (a.Cout / 8) + cg) * (a.H >> 1) + (y >> 1)) * (size_t)(a.W >> 1) + (x >> 1)) * 8;
+                                float vv[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) vv[j] = __uint_as_float(r[g2 * 8 + j]) + bias_s[cg * 8 + j];
+                                if (a.res_mode != 0) {
+                                    const __half* hh = reinterpret_cast<const __half*>(&rcur[gl]);
+                                    const __half* ll = reinterpret_cast<const __half*>(&rcur[G + gl]);
+                                    float rr[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) rr[j] = __half2float(hh[j]) + (a.res_split ? __half2float(ll[j]) : 0.f);
+                                    if (a.res_mode == 1) {
+#pragma unroll
+                                        for (int j = 0; j < 8; j++) vv[j] += rr[j];
+                                    }
+                                    if (a.act_mode == 1) {
+#pragma unroll
+                                        for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
+                                    } else if (a.act_mode == 2) {
+#pragma unroll
+                                        for (int j = 0; j < 8; j++) vv[j] = vv[j] < 0.f ? vv[j] * slope_s[cg * 8 + j] : vv[j];
+                                    }
+                                    if (a.res_mode == 2) {
+#pragma unroll
+                                        for (int j = 0; j < 8; j++) vv[j] += rr[j];
+                                    }
+                                } else if (a.act_mode == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
+                                } else if (a.act_mode == 2) {
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) vv[j] = vv[j] < 0.f ? vv[j] * slope_s[cg * 8 + j] : vv[j];
+                                }
+                                __half hi[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) hi[j] = __float2half_rn(vv[j]);
+                                *reinterpret_cast<uint4*>(a.out + ooff) =
+                                    make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+                                if (a.split_out) {
+                                    __half lo[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) lo[j] = __float2half_rn(vv[j] - __half2float(hi[j]));
+                                    *reinterpret_cast<uint4*>(a.out + a.out_plane + ooff) =
+                                        make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
                                 }
                             }
-                            if (a.act_mode == 1) {
-#pragma unroll
-                                for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
-                            } else if (a.act_mode == 2) {
-#pragma unroll
-                                for (int j = 0; j < 8; j++) { float s = __ldg(a.prelu + cg * 8 + j); vv[j] = vv[j] < 0.f ? vv[j] * s : vv[j]; }
-                            }
-                            if (a.res_mode == 2) {
-                                uint4 rh = __ldg(reinterpret_cast<const uint4*>(a.res + off));
-                                const __half* h = reinterpret_cast<const __half*>(&rh);
-#pragma unroll
-                                for (int j = 0; j < 8; j++) vv[j] += __half2float(h[j]);
-                                if (a.res_split) {
-                                    uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
-                                    const __half* l = reinterpret_cast<const __half*>(&rl);
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) vv[j] += __half2float(l[j]);
-                                }
-                            }
-                            __half hi[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) hi[j] = __float2half_rn(vv[j]);
-                            uint4 oh = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-                            *reinterpret_cast<uint4*>(a.out + off) = oh;
-                            if (a.split_out) {
-                                __half lo[8];
-#pragma unroll
-                                for (int j = 0; j < 8; j++) lo[j] = __float2half_rn(vv[j] - __half2float(hi[j]));
-                                uint4 ol = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
-                                *reinterpret_cast<uint4*>(a.out + a.out_plane + off) = ol;
-                            }
-                        }
-                    } else {
-                        // deconv4x4s2 (+ optional PixelShuffle r) epilogue: column n = parity * ocs + oc
-                        // deconv output pixel (2y+py, 2x+px), channel oc; PixelShuffle: oc = qq*r*r + sh*r + sw
-                        const int r = a.ps, rr = r * r;
-                        const int OH = a.H * 2 * r, OW = a.W * 2 * r;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const int n = c0 + j;
-                            const int par = n / a.ocs, oc = n - par * a.ocs;
-                            if (par >= 4 || oc >= a.Cout) continue;
-                            const int py = par >> 1, px = par & 1;
-                            const int qq = oc / rr, sh = (oc - qq * rr) / r, sw = oc % r;
-                            const int oy = (2 * y + py) * r + sh, ox = (2 * x + px) * r + sw;
-                            float val = v[j];
-                            if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
-                            a.out_f32[((size_t)qq * OH + oy) * OW + ox] = val;
                         }
                     }
                 }
+            } else {
+                // deconv4x4s2 (+ optional PixelShuffle r) epilogue: column n = parity * ocs + oc, parity = py*2+px.
+                // deconv output pixel (2y+py, 2x+px), channel oc; PixelShuffle(r): oc = qq*r*r + sh*r + sw lands at
+                // row (2y+py)*r+sh, column (2x+px)*r+sw of plane qq -> for fixed (qq, sh, py) the 2r columns
+                // 2r*x .. 2r*x+2r-1 are contiguous: one 16-byte (r=2) / 8-byte (r=1) store per thread, coalesced per warp.
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
+                if constexpr (N <= 96) {
+                const int r_ = a.ps;
+                const int OH = a.H * 2 * r_, OW = a.W * 2 * r_;
+#pragma unroll 1
+                for (int m = 0; m < MT; m++) {
+                    const int y = y0 + 2 * m + yrow;
+                    const bool valid = xvalid && y < a.H;
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N;
+                    float v[N];
+#pragma unroll
+                    for (int c0 = 0; c0 < N; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(trow + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            float val = __uint_as_float(r[j]) + bias_s[c0 + j];
+                            if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
+                            v[c0 + j] = val;
+                        }
+                    }
+                    if (!valid) continue;
+                    constexpr int OCS = N / 4;
+                    if (r_ == 2) {
+#pragma unroll
+                        for (int oc4 = 0; oc4 < OCS / 4; oc4++) {   // oc4 = qq
+                            if (oc4 * 4 >= a.Cout) break;
+#pragma unroll
+                            for (int sh = 0; sh < 2; sh++)
+#pragma unroll
+                                for (int py = 0; py < 2; py++) {
+                                    const int o0 = oc4 * 4 + sh * 2;  // oc for sw = 0
+                                    float4 w4 = make_float4(v[(py * 2 + 0) * OCS + o0], v[(py * 2 + 0) * OCS + o0 + 1],
+                                                            v[(py * 2 + 1) * OCS + o0], v[(py * 2 + 1) * OCS + o0 + 1]);
+                                    const int oy = (2 * y + py) * 2 + sh;
+                                    *reinterpret_cast<float4*>(a.out_f32 + ((size_t)oc4 * OH + oy) * OW + 4 * x) = w4;
+                                }
+                        }
+                    } else {
+#pragma unroll
+                        for (int oc = 0; oc < OCS; oc++) {
+                            if (oc >= a.Cout) break;
+#pragma unroll
+                            for (int py = 0; py < 2; py++) {
+                                float2 w2 = make_float2(v[(py * 2 + 0) * OCS + oc], v[(py * 2 + 1) * OCS + oc]);
+                                *reinterpret_cast<float2*>(a.out_f32 + ((size_t)oc * OH + 2 * y + py) * OW + 2 * x) = w2;
+                            }
+                        }
+                    }
+                }
+                }  // N <= 96 (deconv instances)
             }
             tc_fence_before();
             __syncwarp();
@@ -334,28 +432,33 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int N, int MT, int STAGES>
+template <int N, int MT, int STAGES, int TAPS>
 static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     constexpr int ROWS = 2 * MT + 2;
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;
-    constexpr int W_BYTES = 9 * 2 * N * 16;
+    constexpr int W_BYTES = TAPS * 2 * N * 16;
     const int nplanes = a.split_in ? 2 : 1;
     const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
-    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256 + 2 * N * sizeof(float);
     if (smem > 227 * 1024) return -2;
     static size_t configured = 0;
     if (smem > configured) {
-        if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+        if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
         configured = smem;
     }
     int ntiles = a.tiles_x * a.tiles_y;
     int grid = ntiles < a.num_sms ? ntiles : a.num_sms;
-    tc_conv3x3_kernel<N, MT, STAGES><<<grid, NTHREADS, smem, st>>>(tm, a);
+    tc_conv3x3_kernel<N, MT, STAGES, TAPS><<<grid, NTHREADS, smem, st>>>(tm, a);
     g_launch_count++;
     return 0;
 }
 
 int tc_conv_tile_rows(int N) { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }
+
+template <int N, int MT, int STAGES>
+static int launch_n(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+    return a.s2 ? launch_t<N, MT, STAGES, 4>(a, tm, st) : launch_t<N, MT, STAGES, 9>(a, tm, st);
+}
 
 int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
@@ -368,7 +471,10 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     if (!a.num_sms) a.num_sms = 148;
     // activation tensor viewed as [planes * C/8][H][W*4] 32-bit words (16 B = one pixel's 8 channels)
     CUtensorMap tm;
-    cuuint64_t dims[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * (a.Cin / 8)};
+    // stride 2: the input is the space-to-depth tensor, 4 sub-images of (H, W) = output size, Cin channels each
+    const int cgroups = (a.s2 ? 4 : 1) * (a.Cin / 8);
+    if (a.out_s2d && ((a.H | a.W) & 1)) return -7;
+    cuuint64_t dims[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups};
     cuuint64_t strides[2] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16};
     cuuint32_t box[3] = {(cuuint32_t)TWP * 4, (cuuint32_t)(2 * MT + 2), 2};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -376,54 +482,72 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -5;
     switch (a.N) {
-        case 32: return launch_t<32, 4, 4>(a, tm, st);
-        case 64: return launch_t<64, 4, 3>(a, tm, st);
-        case 96: return launch_t<96, 2, 3>(a, tm, st);
-        case 128: return launch_t<128, 2, 3>(a, tm, st);
-        case 192: return launch_t<192, 1, 3>(a, tm, st);
+        case 32: return launch_n<32, 4, 4>(a, tm, st);
+        case 48: return launch_n<48, 4, 3>(a, tm, st);
+        case 64: return launch_n<64, 4, 3>(a, tm, st);
+        case 96: return launch_n<96, 2, 3>(a, tm, st);
+        case 128: return launch_n<128, 2, 3>(a, tm, st);
+        case 192: return launch_n<192, 1, 3>(a, tm, st);
         default: return -6;
     }
 }
 
 // ---- layout conversion kernels -------------------------------------------------------------------
-// planar fp32 [C][H][W] -> C8 planar fp16 hi (+lo)
-__global__ void planar_to_c8_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H, int W, int split, size_t plane) {
+// planar fp32 [C][H][W] -> C8 planar fp16 hi (+lo); channels are zero padded to Cpad (multiple of 8).
+// s2d: space-to-depth variant [py*2+px][Cpad/8][H/2][W/2][8] feeding the stride-2 tensor-core conv.
+__global__ void planar_to_c8_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int Cpad, int H, int W, int split, int s2d, size_t plane) {
     size_t HW = (size_t)H * W;
-    size_t n = (size_t)(C / 8) * HW;
+    size_t n = (size_t)(Cpad / 8) * HW;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     size_t cg = i / HW, pix = i - cg * HW;
     __half hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        float v = in[(cg * 8 + j) * HW + pix];
+        int c = (int)cg * 8 + j;
+        float v = c < C ? in[(size_t)c * HW + pix] : 0.f;
         hi[j] = __float2half_rn(v);
         lo[j] = __float2half_rn(v - __half2float(hi[j]));
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-    if (split) *reinterpret_cast<uint4*>(out + plane + i * 8) = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+    size_t o = i;
+    if (s2d) {
+        int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+        o = (((size_t)((y & 1) * 2 + (x & 1)) * (Cpad / 8) + cg) * (H >> 1) + (y >> 1)) * (size_t)(W >> 1) + (x >> 1);
+    }
+    *reinterpret_cast<uint4*>(out + o * 8) = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+    if (split) *reinterpret_cast<uint4*>(out + plane + o * 8) = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
 }
-void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st) {
-    size_t n = (size_t)(C / 8) * H * W;
-    planar_to_c8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, H, W, split, (size_t)C * H * W);
+void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad, int s2d) {
+    if (Cpad <= 0) Cpad = (C + 7) / 8 * 8;
+    size_t n = (size_t)(Cpad / 8) * H * W;
+    planar_to_c8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, Cpad, H, W, split, s2d, (size_t)Cpad * H * W);
     g_launch_count++;
 }
-__global__ void c8_to_planar_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int H, int W, int split, size_t plane) {
+__global__ void c8_to_planar_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int Cpad, int H, int W, int split, int s2d, size_t plane) {
     size_t HW = (size_t)H * W;
-    size_t n = (size_t)(C / 8) * HW;
+    size_t n = (size_t)(Cpad / 8) * HW;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     size_t cg = i / HW, pix = i - cg * HW;
-    uint4 h = *reinterpret_cast<const uint4*>(in + i * 8);
-    uint4 l = split ? *reinterpret_cast<const uint4*>(in + plane + i * 8) : make_uint4(0, 0, 0, 0);
+    size_t o = i;
+    if (s2d) {
+        int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+        o = (((size_t)((y & 1) * 2 + (x & 1)) * (Cpad / 8) + cg) * (H >> 1) + (y >> 1)) * (size_t)(W >> 1) + (x >> 1);
+    }
+    uint4 h = *reinterpret_cast<const uint4*>(in + o * 8);
+    uint4 l = split ? *reinterpret_cast<const uint4*>(in + plane + o * 8) : make_uint4(0, 0, 0, 0);
     const __half* hh = reinterpret_cast<const __half*>(&h);
     const __half* ll = reinterpret_cast<const __half*>(&l);
 #pragma unroll
-    for (int j = 0; j < 8; j++) out[(cg * 8 + j) * HW + pix] = __half2float(hh[j]) + __half2float(ll[j]);
+    for (int j = 0; j < 8; j++) {
+        int c = (int)cg * 8 + j;
+        if (c < C) out[(size_t)c * HW + pix] = __half2float(hh[j]) + __half2float(ll[j]);
+    }
 }
-void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st) {
-    size_t n = (size_t)(C / 8) * H * W;
-    c8_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, H, W, split, (size_t)C * H * W);
+void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st, int Cpad, int s2d) {
+    if (Cpad <= 0) Cpad = (C + 7) / 8 * 8;
+    size_t n = (size_t)(Cpad / 8) * H * W;
+    c8_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, C, Cpad, H, W, split, s2d, (size_t)Cpad * H * W);
     g_launch_count++;
 }
 
@@ -440,6 +564,28 @@ void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<
                         __half h = __float2half_rn(w[((size_t)n * cin + ic) * 9 + tap]);
                         out[((((size_t)kc * 9 + tap) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
                     }
+}
+// conv 3x3 stride 2: w[oc][ic][3][3] -> wpk[4 parities][cinp/16][4 slots][2][N][8]; parity (py,px) of the space-to-depth
+// input, slot (iy*2+ix) <-> tap dy = py ? 2*iy : 1, dx = px ? 2*ix : 1; input channels zero padded to cinp
+void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, std::vector<uint16_t>& out) {
+    const int kcp = cinp / 16;
+    out.assign((size_t)4 * kcp * 4 * 2 * N * 8, 0);
+    for (int par = 0; par < 4; par++) {
+        const int py = par >> 1, px = par & 1;
+        for (int kc = 0; kc < kcp; kc++)
+            for (int iy = 0; iy < (py ? 2 : 1); iy++)
+                for (int ix = 0; ix < (px ? 2 : 1); ix++) {
+                    const int dy = py ? 2 * iy : 1, dx = px ? 2 * ix : 1;
+                    for (int hf = 0; hf < 2; hf++)
+                        for (int n = 0; n < cout; n++)
+                            for (int j = 0; j < 8; j++) {
+                                int ic = kc * 16 + hf * 8 + j;
+                                if (ic >= cin) continue;
+                                __half h = __float2half_rn(w[((size_t)n * cin + ic) * 9 + dy * 3 + dx]);
+                                out[(((((size_t)par * kcp + kc) * 4 + iy * 2 + ix) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
+                            }
+                }
+    }
 }
 // deconv 4x4 s2 p1: w[oc][ic][4][4] -> 3x3-neighbourhood GEMM with n = parity*ocs + oc:
 // out(2y+py, 2x+px) = sum_{dy,dx} in(y-1+dy, x-1+dx) * w[oc][ic][3+py-2dy][3+px-2dx]  for dy-py, dx-px in {0,1}

@@ -26,6 +26,8 @@ struct TcConvArgs {
     int res_mode;           // 0 none, 1 add before activation, 2 add after activation
     int act_mode;           // 0 none, 1 leaky(slope), 2 prelu, 3 sigmoid (deconv epilogue only)
     int ocs, ps;            // deconv: output-channel slots per parity, PixelShuffle factor (1 = none)
+    int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
+    int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
 };
 
@@ -33,10 +35,11 @@ struct TcConvArgs {
 int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st);
 int tc_conv_tile_rows(int N);
 
-void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st);
-void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st);
+void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
+void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
 
 void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out);
+void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, std::vector<uint16_t>& out);
 void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out);
 
 }  // namespace rife

@@ -56,3 +56,13 @@ def test_deconv_pixelshuffle(pkg, cin, cout, ps):
     o_tc, o_ref = pkg.selftest_conv(1, x, wgt, b, split=True, ps=ps)
     mx, tol, bad = _check(o_tc, o_ref, 1)
     assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
+@pytest.mark.parametrize("cin,cout", [(12, 32), (7, 96), (12, 48), (32, 64), (48, 96), (64, 128), (96, 192)])
+def test_conv3x3_stride2(pkg, cin, cout):
+    """Stride-2 conv over the space-to-depth input (block-head convs: narrow fp32-critical inputs padded to 16 ch)."""
+    h, w = 44, 140  # output 22 x 70: two column tiles, ragged rows
+    x, wgt, b, _ = _data(cin, cout, h, w, 9, seed=cin * 7 + cout)
+    o_tc, o_ref = pkg.selftest_conv(2, x, wgt, b, slope=0.2, split=True)
+    mx, tol, bad = _check(o_tc, o_ref, 1)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
