@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -174,6 +175,7 @@ def main():
     else:
         eng.load(md)
     eng.set_option("precision", args.precision)
+    eng.set_option("lanes", args.lanes)
 
     # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
     nframes = PAIRS_PER_STEP + 1
@@ -188,9 +190,12 @@ def main():
     eng.set_option("async", 1)
     torch.cuda.synchronize()
 
+    d_in0 = [dev[i].data_ptr() for i in range(PAIRS_PER_STEP)]
+    d_in1 = [dev[i + 1].data_ptr() for i in range(PAIRS_PER_STEP)]
+    d_out = [t.data_ptr() for t in out_dev]
+
     def step_device():
-        for i in range(PAIRS_PER_STEP):
-            eng.process_ptr(dev[i].data_ptr(), dev[i + 1].data_ptr(), w, h, 0.5, out_dev[i].data_ptr(), device=True)
+        eng.process_batch_ptr(d_in0, d_in1, w, h, [0.5] * PAIRS_PER_STEP, d_out, device=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,7 +280,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
-                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision,
+                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes,
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
                 "gflop_per_frame": GFLOP_PER_FRAME[args.workload],
                 "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0,

@@ -60,8 +60,15 @@ int rife_b200_process_batch(rife_b200_t* handle, int n, const unsigned char* con
                             const unsigned char* const* in1_rgb, int w, int h, const float* timesteps,
                             unsigned char* const* out_rgb);
 
+/* n independent pairs with all buffers in DEVICE memory; pairs are dealt to the handle's concurrent lanes
+ * (option "lanes", default 2) so small layers of different pairs overlap on the GPU */
+int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned char* const* d_in0_rgb,
+                                   const unsigned char* const* d_in1_rgb, int w, int h, const float* timesteps,
+                                   unsigned char* const* d_out_rgb);
+
 /* precision tier: 0 = exact (fp32 CUDA-core path for every layer), 1 = fast (tcgen05 fp16 tensor-core
  * convolutions with split-precision operands where needed).  Default 1 when the model supports it. */
+/* other keys: "lanes" (1-4 concurrent pairs in flight), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path) */
 int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
 
 /* packed-weights path for multi-GPU loading without re-reading the model directory on every rank */

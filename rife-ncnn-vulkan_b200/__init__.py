@@ -34,6 +34,7 @@ def lib():
     L.rife_b200_process.argtypes = [vp, vp, vp, ci, ci, cf, vp]
     L.rife_b200_process_device.argtypes = [vp, vp, vp, ci, ci, cf, vp]
     L.rife_b200_process_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ctypes.POINTER(cf), ctypes.POINTER(vp)]
+    L.rife_b200_process_batch_device.argtypes = L.rife_b200_process_batch.argtypes
     L.rife_b200_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     L.rife_b200_weights_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     L.rife_b200_weights_export.argtypes = [vp, vp, ctypes.c_size_t]
@@ -51,7 +52,7 @@ def lib():
 
 
 EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
-           "rife_b200_process_batch", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
+           "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv",
            "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
 
@@ -113,11 +114,12 @@ class RIFE:
         fn = self._lib.rife_b200_process_device if device else self._lib.rife_b200_process
         self._check(fn(self._h, in0_ptr, in1_ptr, int(w), int(h), float(timestep), out_ptr), "process_ptr")
 
-    def process_batch_ptr(self, in0_ptrs, in1_ptrs, w, h, timesteps, out_ptrs):
+    def process_batch_ptr(self, in0_ptrs, in1_ptrs, w, h, timesteps, out_ptrs, device=False):
         n = len(in0_ptrs)
         VP = ctypes.c_void_p * n
         ts = (ctypes.c_float * n)(*[float(t) for t in timesteps])
-        self._check(self._lib.rife_b200_process_batch(self._h, n, VP(*in0_ptrs), VP(*in1_ptrs), int(w), int(h), ts, VP(*out_ptrs)), "process_batch")
+        fn = self._lib.rife_b200_process_batch_device if device else self._lib.rife_b200_process_batch
+        self._check(fn(self._h, n, VP(*in0_ptrs), VP(*in1_ptrs), int(w), int(h), ts, VP(*out_ptrs)), "process_batch")
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.rife_b200_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)), "set_stream")

@@ -87,6 +87,14 @@ int rife_b200_process_batch(rife_b200_t* h, int n, const unsigned char* const* i
     GUARD_END
 }
 
+int rife_b200_process_batch_device(rife_b200_t* h, int n, const unsigned char* const* in0, const unsigned char* const* in1, int w, int hh, const float* ts,
+                                   unsigned char* const* out) {
+    GUARD_BEGIN
+    if (!h) return RIFE_B200_ERR_ARG;
+    return map_err(h->eng->process_batch_device(n, in0, in1, w, hh, ts, out));
+    GUARD_END
+}
+
 int rife_b200_set_option(rife_b200_t* h, const char* key, int value) {
     GUARD_BEGIN
     if (!h || !key) return RIFE_B200_ERR_ARG;

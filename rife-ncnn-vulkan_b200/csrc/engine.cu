@@ -26,19 +26,31 @@ void DevBuf::release() {
 Engine::Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v4)
     : gpuid_(gpuid), tta_(tta), ttat_(tta_temporal), uhd_(uhd), v2_(v2), v4_(v4) {}
 
+void Lane::release() {
+    for (auto& r : run) { delete r; r = nullptr; }
+    for (int i = 0; i < 8; i++) { pad0[i].release(); pad1[i].release(); tmp[i].release(); }
+    for (int i = 0; i < 2; i++) { ts[i].release(); tsr[i].release(); for (auto& c : ctx[i]) c.release(); }
+    for (auto& a : flow) for (auto& b : a) b.release();
+    for (auto& a : flowr) for (auto& b : a) b.release();
+    for (auto& b : outp) b.release();
+    if (done) cudaEventDestroy(done);
+    if (st) cudaStreamDestroy(st);
+    done = nullptr;
+    st = nullptr;
+}
+
 Engine::~Engine() {
     cudaSetDevice(gpuid_);
-    if (st_) cudaStreamSynchronize(st_);
-    for (auto& r : run_) delete r;
+    cudaDeviceSynchronize();
+    // borrowers first, the weight-owning lane 0 last
+    for (size_t i = lanes_.size(); i-- > 0;) { lanes_[i]->release(); delete lanes_[i]; }
     for (auto& b : u8_) b.release();
-    for (int i = 0; i < 8; i++) { pad0_[i].release(); pad1_[i].release(); tmp_[i].release(); }
-    for (int i = 0; i < 2; i++) { ts_[i].release(); tsr_[i].release(); for (auto& c : ctx_[i]) c.release(); }
-    for (auto& a : flow_) for (auto& b : a) b.release();
-    for (auto& a : flowr_) for (auto& b : a) b.release();
-    for (auto& b : outp_) b.release();
-    for (auto& p : pinned_) if (p) cudaFreeHost(p);
-    for (auto& e : ev_) if (e) cudaEventDestroy(e);
-    if (st_) cudaStreamDestroy(st_);
+    for (int i = 0; i < kSlots; i++) {
+        if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
+        if (ev_comp_[i]) cudaEventDestroy(ev_comp_[i]);
+        if (ev_d2h_[i]) cudaEventDestroy(ev_d2h_[i]);
+    }
+    if (ev_entry_) cudaEventDestroy(ev_entry_);
     for (auto& s : st_copy_) if (s) cudaStreamDestroy(s);
 }
 
@@ -46,9 +58,30 @@ int Engine::init() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || gpuid_ < 0 || gpuid_ >= n) { last_error = "no such CUDA device"; return -2; }
     if (cudaSetDevice(gpuid_) != cudaSuccess) { last_error = "cudaSetDevice failed"; return -2; }
-    if (cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking) != cudaSuccess) { last_error = "stream creation failed"; return -2; }
     for (auto& s : st_copy_) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    for (auto& e : ev_) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (int i = 0; i < kSlots; i++) {
+        cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp_[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_d2h_[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ev_entry_, cudaEventDisableTiming);
+    return make_lanes(1);
+}
+
+// (re)creates the lanes; lane 0 keeps (owns) the weights, the others borrow them
+int Engine::make_lanes(int n) {
+    if (n < 1) n = 1;
+    if (n > 4) n = 4;
+    while ((int)lanes_.size() > n) { lanes_.back()->release(); delete lanes_.back(); lanes_.pop_back(); }
+    while ((int)lanes_.size() < n) {
+        Lane* L = new Lane();
+        if (cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking) != cudaSuccess) { delete L; last_error = "stream creation failed"; return -2; }
+        cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming);
+        if (!lanes_.empty())
+            for (int i = 0; i < 3; i++)
+                if (lanes_[0]->run[i]) { L->run[i] = new NetRunner(); L->run[i]->share_from(*lanes_[0]->run[i]); }
+        lanes_.push_back(L);
+    }
     return 0;
 }
 
@@ -108,17 +141,21 @@ int Engine::load_packed(const void* data, size_t bytes) {
         std::string err;
         nets_[i] = Net();
         if (parse_net(ptxt, bbin, kNetNames[i], nets_[i], err)) { last_error = err; return -3; }
-        delete run_[i];
-        run_[i] = new NetRunner();
-        run_[i]->tc_mode = precision_;
+        cudaDeviceSynchronize();
+        for (size_t li = lanes_.size(); li-- > 0;) { delete lanes_[li]->run[i]; lanes_[li]->run[i] = nullptr; }
+        NetRunner* r0 = new NetRunner();
+        lanes_[0]->run[i] = r0;
+        r0->tc_mode = precision_;
         {
             cudaDeviceProp prop;
-            if (cudaGetDeviceProperties(&prop, gpuid_) == cudaSuccess) run_[i]->num_sms = prop.multiProcessorCount;
+            if (cudaGetDeviceProperties(&prop, gpuid_) == cudaSuccess) r0->num_sms = prop.multiProcessorCount;
         }
-        if (run_[i]->init(&nets_[i], err)) { last_error = err; return -3; }
+        if (r0->init(&nets_[i], err)) { last_error = err; return -3; }
+        for (size_t li = 1; li < lanes_.size(); li++) { lanes_[li]->run[i] = new NetRunner(); lanes_[li]->run[i]->share_from(*r0); }
     }
     packed_.assign(p, bytes);
     loaded_ = true;
+    if ((int)lanes_.size() != nlanes_) return make_lanes(nlanes_);
     return 0;
 }
 
@@ -126,11 +163,13 @@ int Engine::set_option(const std::string& key, int value) {
     std::lock_guard<std::mutex> lk(mu_);
     if (key == "precision") {  // 0 exact fp32, 1 tensor cores + split-fp16 activations, 2 tensor cores + plain fp16 activations
         precision_ = value;
-        for (auto& r : run_) if (r) { r->tc_mode = value; r->clear_plans(); }
+        cudaDeviceSynchronize();
+        for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->tc_mode = value; r->clear_plans(); }
         return 0;
     }
+    if (key == "lanes") { nlanes_ = value; cudaDeviceSynchronize(); return loaded_ ? make_lanes(value) : 0; }
     if (key == "async") { async_ = value != 0; return 0; }
-    if (key == "fuse") { for (auto& r : run_) if (r) r->fuse = value != 0; return 0; }
+    if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
     last_error = "unknown option " + key;
     return -1;
 }
@@ -151,83 +190,111 @@ int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, f
     if (t == 1.f) { if (out != in1) memcpy(out, in1, n); return 0; }
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
+    Lane& L = *lanes_[0];
     for (int i = 0; i < 3; i++)
         if (u8_[i].ensure(n)) { last_error = "cudaMalloc failed"; return -2; }
-    cudaMemcpyAsync(u8_[0].p, in0, n, cudaMemcpyHostToDevice, st_);
-    cudaMemcpyAsync(u8_[1].p, in1, n, cudaMemcpyHostToDevice, st_);
-    int r = run_device(u8_[0].u8(), u8_[1].u8(), w, h, t, u8_[2].u8(), st_);
+    cudaMemcpyAsync(u8_[0].p, in0, n, cudaMemcpyHostToDevice, L.st);
+    cudaMemcpyAsync(u8_[1].p, in1, n, cudaMemcpyHostToDevice, L.st);
+    int r = run_device(L, u8_[0].u8(), u8_[1].u8(), w, h, t, u8_[2].u8(), L.st);
     if (r) return r;
-    cudaMemcpyAsync(out, u8_[2].p, n, cudaMemcpyDeviceToHost, st_);
-    cudaError_t e = cudaStreamSynchronize(st_);
+    cudaMemcpyAsync(out, u8_[2].p, n, cudaMemcpyDeviceToHost, L.st);
+    cudaError_t e = cudaStreamSynchronize(L.st);
     if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
 int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out) {
-    if (!d_in0 || !d_in1 || !d_out || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
+    const uint8_t* a[1] = {d_in0};
+    const uint8_t* b[1] = {d_in1};
+    uint8_t* o[1] = {d_out};
+    return process_batch_device(1, a, b, w, h, &t, o);
+}
+
+// Frames already in device memory.  Pairs are dealt round-robin to the lanes; when the caller supplied a stream
+// (set_stream) every lane first waits for that stream and the stream finally waits for every lane, so events the
+// caller records on it bracket all of the work.
+int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out) {
+    if (n < 0 || !d_in0 || !d_in1 || !d_out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
     if (!loaded_) { last_error = "process before load"; return -4; }
-    size_t n = (size_t)w * h * 3;
+    size_t nb = (size_t)w * h * 3;
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
-    cudaStream_t st = use_user_stream_ ? user_stream_ : st_;
-    if (t == 0.f || t == 1.f) {
-        cudaMemcpyAsync(d_out, t == 0.f ? d_in0 : d_in1, n, cudaMemcpyDeviceToDevice, st);
-    } else {
-        int r = run_device(d_in0, d_in1, w, h, t, d_out, st);
-        if (r) return r;
+    const int nl = (int)lanes_.size();
+    if (use_user_stream_) {
+        cudaEventRecord(ev_entry_, user_stream_);
+        for (int l = 0; l < nl && l < n; l++) cudaStreamWaitEvent(lanes_[l]->st, ev_entry_, 0);
+    }
+    for (int i = 0; i < n; i++) {
+        if (!d_in0[i] || !d_in1[i] || !d_out[i]) { last_error = "null frame pointer"; return -1; }
+        Lane& L = *lanes_[i % nl];
+        if (ts[i] == 0.f || ts[i] == 1.f) {
+            cudaMemcpyAsync(d_out[i], ts[i] == 0.f ? d_in0[i] : d_in1[i], nb, cudaMemcpyDeviceToDevice, L.st);
+        } else {
+            int r = run_device(L, d_in0[i], d_in1[i], w, h, ts[i], d_out[i], L.st);
+            if (r) return r;
+        }
+    }
+    for (int l = 0; l < nl && l < n; l++) {
+        cudaEventRecord(lanes_[l]->done, lanes_[l]->st);
+        if (use_user_stream_) cudaStreamWaitEvent(user_stream_, lanes_[l]->done, 0);
     }
     if (async_) return 0;
-    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaSuccess;
+    for (int l = 0; l < nl && l < n; l++) { cudaError_t e2 = cudaStreamSynchronize(lanes_[l]->st); if (e2 != cudaSuccess) e = e2; }
+    if (use_user_stream_) { cudaError_t e2 = cudaStreamSynchronize(user_stream_); if (e2 != cudaSuccess) e = e2; }
     if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
-// Pipelined stream path: pair i+1 uploads while pair i computes and pair i-1 downloads (pinned host memory
-// makes the copies truly asynchronous; pageable memory still works, the driver then stages synchronously).
+// Host frames, pipelined: slot s = i mod (2 * lanes) owns three device frame buffers; H2D runs on one copy stream,
+// compute on lane i mod lanes, D2H on the other copy stream, chained with events (pinned host memory makes the copies
+// truly asynchronous; pageable memory still works, the driver then stages synchronously).
 int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out) {
     if (n < 0 || !in0 || !in1 || !out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
     if (!loaded_) { last_error = "process before load"; return -4; }
     size_t nb = (size_t)w * h * 3;
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
-    for (auto& b : u8_)
-        if (b.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
-    // events: ev_[0..1] h2d done (per set), ev_[2..3] compute done, ev_[4..5] d2h done
+    const int nl = (int)lanes_.size();
+    const int nslots = 2 * nl <= kSlots ? 2 * nl : kSlots;
+    for (int i = 0; i < 3 * nslots; i++)
+        if (u8_[i].ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
+    std::vector<int> used(nslots, 0);
     for (int i = 0; i < n; i++) {
-        int s = i & 1;
         if (!in0[i] || !in1[i] || !out[i]) { last_error = "null frame pointer"; return -1; }
         if (ts[i] == 0.f || ts[i] == 1.f) {
-            // copies must not overtake queued work that reads/writes out[] ordering is per pair, so a host copy is safe after sync
-            cudaStreamSynchronize(st_copy_[1]);
-            memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);
+            memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);  // host-side copy, touches nothing queued
             continue;
         }
+        const int s = i % nslots;
+        Lane& L = *lanes_[i % nl];
         uint8_t* d0 = u8_[s * 3 + 0].u8();
         uint8_t* d1 = u8_[s * 3 + 1].u8();
         uint8_t* dout = u8_[s * 3 + 2].u8();
-        if (i >= 2) cudaStreamWaitEvent(st_copy_[0], ev_[2 + s], 0);  // inputs of set s free once its compute finished
+        if (used[s]) cudaStreamWaitEvent(st_copy_[0], ev_comp_[s], 0);  // inputs of slot s are free once its compute finished
         cudaMemcpyAsync(d0, in0[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
         cudaMemcpyAsync(d1, in1[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
-        cudaEventRecord(ev_[s], st_copy_[0]);
-        cudaStreamWaitEvent(st_, ev_[s], 0);
-        if (i >= 2) cudaStreamWaitEvent(st_, ev_[4 + s], 0);  // output buffer of set s downloaded
-        int r = run_device(d0, d1, w, h, ts[i], dout, st_);
+        cudaEventRecord(ev_h2d_[s], st_copy_[0]);
+        cudaStreamWaitEvent(L.st, ev_h2d_[s], 0);
+        if (used[s]) cudaStreamWaitEvent(L.st, ev_d2h_[s], 0);  // output buffer of slot s has been downloaded
+        int r = run_device(L, d0, d1, w, h, ts[i], dout, L.st);
         if (r) return r;
-        cudaEventRecord(ev_[2 + s], st_);
-        cudaStreamWaitEvent(st_copy_[1], ev_[2 + s], 0);
+        cudaEventRecord(ev_comp_[s], L.st);
+        cudaStreamWaitEvent(st_copy_[1], ev_comp_[s], 0);
         cudaMemcpyAsync(out[i], dout, nb, cudaMemcpyDeviceToHost, st_copy_[1]);
-        cudaEventRecord(ev_[4 + s], st_copy_[1]);
+        cudaEventRecord(ev_d2h_[s], st_copy_[1]);
+        used[s] = 1;
     }
-    cudaError_t e0 = cudaStreamSynchronize(st_copy_[0]);
-    cudaError_t e1 = cudaStreamSynchronize(st_);
-    cudaError_t e2 = cudaStreamSynchronize(st_copy_[1]);
-    cudaError_t e = e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
+    cudaError_t e = cudaStreamSynchronize(st_copy_[0]);
+    for (Lane* L : lanes_) { cudaError_t e2 = cudaStreamSynchronize(L->st); if (e2 != cudaSuccess) e = e2; }
+    cudaError_t e3 = cudaStreamSynchronize(st_copy_[1]);
+    if (e3 != cudaSuccess) e = e3;
     if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
-int Engine::run_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
-    int r = v4_ ? run_v4(d_in0, d_in1, w, h, t, d_out, st) : run_v1v2(d_in0, d_in1, w, h, d_out, st);
+int Engine::run_device(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
+    int r = v4_ ? run_v4(L, d_in0, d_in1, w, h, t, d_out, st) : run_v1v2(L, d_in0, d_in1, w, h, d_out, st);
     if (r) return r;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
@@ -237,31 +304,31 @@ int Engine::run_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h,
 typedef std::vector<std::pair<std::string, Tensor>> Inputs;
 
 // ---- rife-v4 / v4.6: rife.cpp:3204-4401 -------------------------------------------------------------------
-int Engine::run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
+int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
     const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;  // rife.cpp:3229-3230
     const size_t plane = (size_t)wp * hp;
-    NetRunner& F = *run_[0];
+    NetRunner& F = *L.run[0];
     std::string err;
     std::vector<Tensor> o;
     const int nti = tta_ ? 8 : 1;
     Tensor I0[8], I1[8], T[2], TR[2];
     for (int ti = 0; ti < nti; ti++) {
-        if (pad0_[ti].ensure(3 * plane * 4) || pad1_[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
-        launch_preproc(d_in0, w, h, pad0_[ti].f(), wp, hp, ti, st);  // rife.cpp:4152-4211 / 3253-3413
-        launch_preproc(d_in1, w, h, pad1_[ti].f(), wp, hp, ti, st);
+        if (L.pad0[ti].ensure(3 * plane * 4) || L.pad1[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
+        launch_preproc(d_in0, w, h, L.pad0[ti].f(), wp, hp, ti, st);  // rife.cpp:4152-4211 / 3253-3413
+        launch_preproc(d_in1, w, h, L.pad1[ti].f(), wp, hp, ti, st);
         int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
-        I0[ti] = Tensor::chw(pad0_[ti].f(), 3, th, tw);
-        I1[ti] = Tensor::chw(pad1_[ti].f(), 3, th, tw);
+        I0[ti] = Tensor::chw(L.pad0[ti].f(), 3, th, tw);
+        I1[ti] = Tensor::chw(L.pad1[ti].f(), 3, th, tw);
     }
-    ts_[0].ensure(plane * 4);
-    launch_fill(ts_[0].f(), plane, t, st);  // full padded plane, rife.cpp:4213-4214
-    T[0] = Tensor::chw(ts_[0].f(), 1, hp, wp);
-    T[1] = Tensor::chw(ts_[0].f(), 1, wp, hp);  // rife.cpp:3313-3316 (same constant, transposed extent)
+    L.ts[0].ensure(plane * 4);
+    launch_fill(L.ts[0].f(), plane, t, st);  // full padded plane, rife.cpp:4213-4214
+    T[0] = Tensor::chw(L.ts[0].f(), 1, hp, wp);
+    T[1] = Tensor::chw(L.ts[0].f(), 1, wp, hp);  // rife.cpp:3313-3316 (same constant, transposed extent)
     if (ttat_) {
-        tsr_[0].ensure(plane * 4);
-        launch_fill(tsr_[0].f(), plane, 1.f - t, st);
-        TR[0] = Tensor::chw(tsr_[0].f(), 1, hp, wp);
-        TR[1] = Tensor::chw(tsr_[0].f(), 1, wp, hp);
+        L.tsr[0].ensure(plane * 4);
+        launch_fill(L.tsr[0].f(), plane, 1.f - t, st);
+        TR[0] = Tensor::chw(L.tsr[0].f(), 1, hp, wp);
+        TR[1] = Tensor::chw(L.tsr[0].f(), 1, wp, hp);
     }
     static const char* kFlow[4] = {"flow0", "flow1", "flow2", "flow3"};
 
@@ -281,13 +348,13 @@ int Engine::run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, flo
                 Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], fl[k][ti]});
                 if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
-                fl[fi][ti] = keep(o[0], flow_[fi][ti], st);
+                fl[fi][ti] = keep(o[0], L.flow[fi][ti], st);
             }
             if (ttat_) {
                 Inputs in = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], flr[k][ti]});
                 if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
-                flr[fi][ti] = keep(o[0], flowr_[fi][ti], st);
+                flr[fi][ti] = keep(o[0], L.flowr[fi][ti], st);
                 // rife.cpp:3476-3512 / 4277-4312
                 launch_temporal_merge_v2(fl[fi][ti].p, flr[fi][ti].p, (size_t)fl[fi][ti].h * fl[fi][ti].w, 1, st);
             }
@@ -308,13 +375,13 @@ int Engine::run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, flo
         Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
         for (int k = 0; k < 4; k++) in.push_back({kFlow[k], fl[k][ti]});
         if (F.run(in, {"out0"}, o, st, err)) { last_error = err; return -5; }
-        ins[ti] = keep(o[0], outp_[ti], st).p;
+        ins[ti] = keep(o[0], L.outp[ti], st).p;
         orients[ti] = ti;
         if (ttat_) {
             Inputs inr = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
             for (int k = 0; k < 4; k++) inr.push_back({kFlow[k], flr[k][ti]});
             if (F.run(inr, {"out0"}, o, st, err)) { last_error = err; return -5; }
-            ins[nti + ti] = keep(o[0], outp_[8 + ti], st).p;
+            ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
             orients[nti + ti] = ti;
         }
     }
@@ -324,32 +391,32 @@ int Engine::run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, flo
 }
 
 // ---- rife / rife-HD / rife-UHD / rife-anime (v1), rife-v2.x / v3.x (v2): rife.cpp:1214-2460 ----------------
-int Engine::run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st) {
+int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st) {
     const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
     const size_t plane = (size_t)wp * hp;
-    NetRunner& F = *run_[0];
-    NetRunner& C = *run_[1];
-    NetRunner& U = *run_[2];
+    NetRunner& F = *L.run[0];
+    NetRunner& C = *L.run[1];
+    NetRunner& U = *L.run[2];
     std::string err;
     std::vector<Tensor> o;
     const int nti = tta_ ? 8 : 1;
     Tensor I0[8], I1[8];
     for (int ti = 0; ti < nti; ti++) {
-        if (pad0_[ti].ensure(3 * plane * 4) || pad1_[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
-        launch_preproc(d_in0, w, h, pad0_[ti].f(), wp, hp, ti, st);
-        launch_preproc(d_in1, w, h, pad1_[ti].f(), wp, hp, ti, st);
+        if (L.pad0[ti].ensure(3 * plane * 4) || L.pad1[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
+        launch_preproc(d_in0, w, h, L.pad0[ti].f(), wp, hp, ti, st);
+        launch_preproc(d_in1, w, h, L.pad1[ti].f(), wp, hp, ti, st);
         int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
-        I0[ti] = Tensor::chw(pad0_[ti].f(), 3, th, tw);
-        I1[ti] = Tensor::chw(pad1_[ti].f(), 3, th, tw);
+        I0[ti] = Tensor::chw(L.pad0[ti].f(), 3, th, tw);
+        I1[ti] = Tensor::chw(L.pad1[ti].f(), 3, th, tw);
     }
     // flownet(a, b) -> flow at half resolution; uhd: rife.cpp:2212-2229
     auto flownet = [&](const Tensor& a, const Tensor& b, DevBuf& dst, Tensor& flow) -> int {
         if (uhd_) {
             Tensor ad = Tensor::chw(nullptr, 3, (int)(a.h * 0.5f), (int)(a.w * 0.5f)), bd = ad;
-            tmp_[0].ensure(ad.count() * 4);
-            tmp_[1].ensure(ad.count() * 4);
-            ad.p = tmp_[0].f();
-            bd.p = tmp_[1].f();
+            L.tmp[0].ensure(ad.count() * 4);
+            L.tmp[1].ensure(ad.count() * 4);
+            ad.p = L.tmp[0].f();
+            bd.p = L.tmp[1].f();
             launch_interp_bilinear(a.p, 3, a.h, a.w, ad.p, ad.h, ad.w, st);
             launch_interp_bilinear(b.p, 3, b.h, b.w, bd.p, bd.h, bd.w, st);
             Inputs in = {{"input0", ad}, {"input1", bd}};
@@ -369,7 +436,7 @@ int Engine::run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, u
     };
     Tensor fl[8], flr[8];
     for (int ti = 0; ti < nti; ti++)
-        if (flownet(I0[ti], I1[ti], flow_[0][ti], fl[ti])) return -5;
+        if (flownet(I0[ti], I1[ti], L.flow[0][ti], fl[ti])) return -5;
     auto merge = [&](int ti) {
         size_t n = (size_t)fl[ti].h * fl[ti].w;
         if (v2_) launch_temporal_merge_v2(fl[ti].p, flr[ti].p, n, 0, st);  // rife.cpp:2285-2306
@@ -377,7 +444,7 @@ int Engine::run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, u
     };
     if (ttat_)
         for (int ti = 0; ti < nti; ti++) {
-            if (flownet(I1[ti], I0[ti], flowr_[0][ti], flr[ti])) return -5;
+            if (flownet(I1[ti], I0[ti], L.flowr[0][ti], flr[ti])) return -5;
             merge(ti);
         }
     if (tta_) {  // rife.cpp:1541-1719, reversed :1721-1896, second merge :1898-1949
@@ -404,25 +471,25 @@ int Engine::run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, u
         {   // rife.cpp:2335-2351
             Inputs in = {{"input.1", I0[ti]}, {"flow.0", f0}};
             if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
-            for (int k = 0; k < 4; k++) c0[k] = keep(o[k], ctx_[0][k], st);
+            for (int k = 0; k < 4; k++) c0[k] = keep(o[k], L.ctx[0][k], st);
         }
         {   // rife.cpp:2352-2368
             Inputs in = {{"input.1", I1[ti]}, {v2_ ? "flow.0" : "flow.1", f1}};
             if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
-            for (int k = 0; k < 4; k++) c1[k] = keep(o[k], ctx_[1][k], st);
+            for (int k = 0; k < 4; k++) c1[k] = keep(o[k], L.ctx[1][k], st);
         }
         {   // rife.cpp:2372-2388
             Inputs in = {{"img0", I0[ti]}, {"img1", I1[ti]}, {"flow", fl[ti]}, {"3", c0[0]}, {"4", c0[1]}, {"5", c0[2]}, {"6", c0[3]},
                          {"7", c1[0]}, {"8", c1[1]}, {"9", c1[2]}, {"10", c1[3]}};
             if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
-            ins[ti] = (tta_ || ttat_) ? keep(o[0], outp_[ti], st).p : o[0].p;
+            ins[ti] = (tta_ || ttat_) ? keep(o[0], L.outp[ti], st).p : o[0].p;
             orients[ti] = ti;
         }
         if (ttat_) {  // rife.cpp:2391-2409
             Inputs in = {{"img0", I1[ti]}, {"img1", I0[ti]}, {"flow", flr[ti]}, {"3", c1[0]}, {"4", c1[1]}, {"5", c1[2]}, {"6", c1[3]},
                          {"7", c0[0]}, {"8", c0[1]}, {"9", c0[2]}, {"10", c0[3]}};
             if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
-            ins[nti + ti] = keep(o[0], outp_[8 + ti], st).p;
+            ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
             orients[nti + ti] = ti;
         }
     }

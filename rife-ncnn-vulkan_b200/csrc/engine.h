@@ -22,6 +22,19 @@ struct DevBuf {
     uint8_t* u8() const { return (uint8_t*)p; }
 };
 
+// one concurrent execution context: own stream, own plans (arenas) and scratch; weights are shared
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    NetRunner* run[3] = {nullptr, nullptr, nullptr};
+    DevBuf pad0[8], pad1[8], ts[2], tsr[2];
+    DevBuf flow[4][8], flowr[4][8];
+    DevBuf outp[16];
+    DevBuf ctx[2][4];
+    DevBuf tmp[8];
+    void release();
+};
+
 class Engine {
 public:
     Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v4);
@@ -33,15 +46,17 @@ public:
     int process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out);
     int process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out);
     int process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out);
+    int process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out);
     int set_option(const std::string& key, int value);
     void set_stream(cudaStream_t s) { std::lock_guard<std::mutex> lk(mu_); user_stream_ = s; use_user_stream_ = s != nullptr; }
     std::string last_error;
 
 private:
     int finish_load();
-    int run_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
-    int run_v4(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
-    int run_v1v2(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st);
+    int run_device(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
+    int run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
+    int run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st);
+    int make_lanes(int n);
     Tensor keep(const Tensor& t, DevBuf& b, cudaStream_t st);  // copy a plan-owned tensor into an engine buffer
 
     int gpuid_;
@@ -52,20 +67,15 @@ private:
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;
     Net nets_[3];           // flownet, contextnet, fusionnet
-    NetRunner* run_[3] = {nullptr, nullptr, nullptr};
+    std::vector<Lane*> lanes_;
+    int nlanes_ = 2;
     std::string packed_;    // serialized model (param text + bin bytes per net)
-    cudaStream_t st_ = nullptr, st_copy_[2] = {nullptr, nullptr};
-    cudaEvent_t ev_[8] = {};
+    cudaStream_t st_copy_[2] = {nullptr, nullptr};
+    static const int kSlots = 8;
+    cudaEvent_t ev_h2d_[kSlots] = {}, ev_comp_[kSlots] = {}, ev_d2h_[kSlots] = {}, ev_entry_ = nullptr;
     std::mutex mu_;
     // device buffers
-    DevBuf u8_[6];          // staged in0,in1,out (x2 for the pipelined batch path)
-    void* pinned_[6] = {};  // pinned host staging
-    size_t pinned_cap_[6] = {};
-    DevBuf pad0_[8], pad1_[8], ts_[2], tsr_[2];
-    DevBuf flow_[4][8], flowr_[4][8];
-    DevBuf outp_[16];
-    DevBuf ctx_[2][4];
-    DevBuf tmp_[8];
+    DevBuf u8_[3 * kSlots];  // staged in0,in1,out per pipeline slot
 };
 
 }  // namespace rife

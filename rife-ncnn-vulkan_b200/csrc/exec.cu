@@ -30,7 +30,7 @@ static float* upload(const std::vector<float>& v, std::string& err) {
 }
 
 NetRunner::~NetRunner() {
-    for (auto& w : dw_) {
+    if (owns_) for (auto& w : dw_own_) {
         cudaFree(w.wT);
         cudaFree(w.bias);
         cudaFree(w.slope);
@@ -53,10 +53,12 @@ size_t NetRunner::arena_bytes() const {
 
 int NetRunner::init(const Net* net, std::string& err) {
     net_ = net;
-    dw_.assign(net->layers.size(), DeviceWeights());
+    dw_own_.assign(net->layers.size(), DeviceWeights());
+    dwp_ = &dw_own_;
+    owns_ = true;
     for (size_t li = 0; li < net->layers.size(); li++) {
         const Layer& L = net->layers[li];
-        DeviceWeights& W = dw_[li];
+        DeviceWeights& W = dw_own_[li];
         if (L.type == "Convolution") {
             int cout = L.geti(0, 0), kw = L.geti(1, 0), kh = L.geti(11, kw);
             int kk = kw * kh;
@@ -243,7 +245,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
                 }
             }
         }
-        if (tc_mode > 0 && dw_[l].wpk && plan.external_slot[L.tops[0]] < 0) {
+        if (tc_mode > 0 && (*dwp_)[l].wpk && plan.external_slot[L.tops[0]] < 0) {
             int own_act = L.geti(9, 0);
             if (L.type == "Convolution") {
                 bool ok = own_act == 0 || (own_act == 2 && s.fused_act_layer < 0 && s.fused_add_blob < 0);
@@ -366,7 +368,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
         for (Step& s : plan.steps) {
             if (s.kind != 1) continue;
             const Layer& L = net.layers[s.layer];
-            const DeviceWeights& W = dw_[s.layer];
+            const DeviceWeights& W = (*dwp_)[s.layer];
             const Tensor& x = plan.blobs[L.bottoms[0]];
             bool ok = eoff[L.bottoms[0]] == 0 && x.dims == 3 && x.c == W.cin;
             if (s.fused_add_blob >= 0 && eoff[s.fused_add_blob] != 0) ok = false;
@@ -387,7 +389,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
         }
         // a residual must be in plain C8 form: demote stride-2 consumers whose input doubles as a residual
         for (Step& s : plan.steps)
-            if (s.kind == 1 && dw_[s.layer].tc_s2 && c8_used_s1[root[net.layers[s.layer].bottoms[0]]]) {
+            if (s.kind == 1 && (*dwp_)[s.layer].tc_s2 && c8_used_s1[root[net.layers[s.layer].bottoms[0]]]) {
                 plan.c8_s2d[root[net.layers[s.layer].bottoms[0]]] = 0;
                 s.kind = 0;
             }
@@ -516,7 +518,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
     }
     if (s.kind == 1) {
         const Layer& L = net.layers[s.layer];
-        const DeviceWeights& W = dw_[s.layer];
+        const DeviceWeights& W = (*dwp_)[s.layer];
         const Tensor& x = plan.blobs[L.bottoms[0]];
         const Tensor& o = plan.blobs[s.out_blob];
         TcConvArgs a;
@@ -549,7 +551,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
                 const Layer& A = net.layers[s.fused_act_layer];
                 if (A.type == "ReLU") { a.act_mode = 1; a.slope = A.getf(0, 0.f); }
                 else if (A.slope.size() == 1) { a.act_mode = 1; a.slope = A.slope[0]; }
-                else { a.act_mode = 2; a.prelu = dw_[s.fused_act_layer].slope; }
+                else { a.act_mode = 2; a.prelu = (*dwp_)[s.fused_act_layer].slope; }
             }
         } else {
             a.epi = TC_EPI_DECONV;
@@ -563,7 +565,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
         return 0;
     }
     const Layer& L = net.layers[s.layer];
-    const DeviceWeights& W = dw_[s.layer];
+    const DeviceWeights& W = (*dwp_)[s.layer];
     const std::string& T = L.type;
     if (T == "Split" || T == "Crop") return 0;
     auto in = [&](int i) -> const Tensor& { return plan.blobs[L.bottoms[i]]; };
@@ -591,7 +593,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
                 a.post_p0 = slope;
             } else {  // PReLU
                 if (A.slope.size() == 1) { a.post_act = 2; a.post_p0 = A.slope[0]; }
-                else { a.post_act = 5; a.post_slope = dw_[s.fused_act_layer].slope; }
+                else { a.post_act = 5; a.post_slope = (*dwp_)[s.fused_act_layer].slope; }
             }
         }
         if (T == "Convolution") {

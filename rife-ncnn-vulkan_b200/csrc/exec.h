@@ -42,6 +42,8 @@ public:
     NetRunner() {}
     ~NetRunner();
     int init(const Net* net, std::string& err);  // uploads weights to the current device
+    // second and further runners of the same net on the same device (concurrent lanes) borrow the owner's weights
+    void share_from(const NetRunner& owner) { net_ = owner.net_; dwp_ = owner.dwp_; owns_ = false; tc_mode = owner.tc_mode; num_sms = owner.num_sms; fuse = owner.fuse; }
     const Net* net() const { return net_; }
     bool fuse = true;  // conv+add+leaky / conv+prelu epilogue fusion
     int tc_mode = 1;   // 0: fp32 CUDA-core kernels only; 1: tcgen05 with split-fp16 (hi+lo) activations; 2: tcgen05, plain fp16
@@ -83,7 +85,9 @@ private:
     int exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string& err);
 
     const Net* net_ = nullptr;
-    std::vector<DeviceWeights> dw_;
+    std::vector<DeviceWeights> dw_own_;
+    const std::vector<DeviceWeights>* dwp_ = nullptr;
+    bool owns_ = true;
     std::map<std::string, std::unique_ptr<Plan>> plans_;
 };
 

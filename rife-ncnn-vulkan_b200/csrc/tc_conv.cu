@@ -90,6 +90,31 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Convergent-issue variants: the whole warp executes the asm, elect.sync picks the one lane that issues.  Keeping the
+// issuing loop free of thread divergence lets ptxas keep descriptors in uniform registers and emit a bare predicated
+// UTCHMMA (a single-lane `if (lane == 0)` loop made it wrap every MMA in an ELECT / BRA.U.ANY lane loop, ~250 cycles each).
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -181,62 +206,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer: all 32 lanes run the loop convergently, one elected lane issues each instruction =====
+        {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major A and B
+            // descriptor words: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+            constexpr uint32_t A_LBO = ((uint32_t)(ROWS * TWP * 16) >> 4) << 16;
+            constexpr uint32_t B_LBO = ((uint32_t)(N * 16) >> 4) << 16;
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
                 const int buf = tcount & 1;
                 const uint32_t aph = (tcount >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);
                 tc_fence_after();
+                const uint32_t acc0 = tmem_base + buf * ACC_COLS;
                 for (int kc = 0; kc < KC; kc++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t wb = st + nplanes * A_PLANE;
+                    const uint32_t a_base = (st >> 4) | A_LBO;
+                    const uint32_t b_base = ((st + nplanes * A_PLANE) >> 4) | B_LBO;
+                    const uint32_t nz = kc != 0;
                     if constexpr (TAPS == 9) {
-#pragma unroll 1
+#pragma unroll
                         for (int tap = 0; tap < 9; tap++) {
                             const int dy = tap / 3, dx = tap - dy * 3;
-                            const uint64_t bdesc = make_desc(wb + tap * (2 * N * 16), N * 16, 128);
+                            const uint32_t b_lo = b_base + (uint32_t)(tap * (2 * N * 16) >> 4);
 #pragma unroll
                             for (int m = 0; m < MT; m++) {
-                                const uint32_t aoff = (uint32_t)(((2 * m + dy) * TWP + dx) * 16);
-                                for (int p = 0; p < nplanes; p++) {
-                                    const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
-                                    umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, (kc | tap | p) != 0);
-                                }
+                                const uint32_t aoff = (uint32_t)((((2 * m + dy) * TWP + dx) * 16) >> 4);
+                                umma_f16_elect(acc0 + m * N, a_base + aoff, DESC_HI, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
+                                if (nplanes == 2) umma_f16_elect(acc0 + m * N, a_base + (uint32_t)(A_PLANE >> 4) + aoff, DESC_HI, b_lo, DESC_HI, idesc, 1u);
                             }
                         }
                     } else {
                         const int par = kc / KCP, py = par >> 1, px = par & 1;
-                        const int nty = py ? 2 : 1, ntx = px ? 2 : 1;
-                        int first = kc == 0;
-#pragma unroll 1
-                        for (int iy = 0; iy < nty; iy++)
-#pragma unroll 1
-                            for (int ix = 0; ix < ntx; ix++) {
+#pragma unroll
+                        for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+                            for (int ix = 0; ix < 2; ix++) {
+                                if (iy > py || ix > px) continue;  // even sub-images contribute one tap per axis (uniform branch)
                                 // odd sub-image: slot 0 = tap d=0 (previous row/col, view offset 0), slot 1 = tap d=2 (view offset 1)
                                 // even sub-image: single slot = tap d=1 (view offset 1)
                                 const int oy = py ? iy : 1, ox = px ? ix : 1;
-                                const uint64_t bdesc = make_desc(wb + (iy * 2 + ix) * (2 * N * 16), N * 16, 128);
+                                const uint32_t b_lo = b_base + (uint32_t)((iy * 2 + ix) * (2 * N * 16) >> 4);
 #pragma unroll
                                 for (int m = 0; m < MT; m++) {
-                                    const uint32_t aoff = (uint32_t)(((2 * m + oy) * TWP + ox) * 16);
-                                    for (int p = 0; p < nplanes; p++) {
-                                        const uint64_t adesc = make_desc(st + p * A_PLANE + aoff, ROWS * TWP * 16, 128);
-                                        umma_f16(tmem_base + buf * ACC_COLS + m * N, adesc, bdesc, idesc, !(first && p == 0));
-                                    }
+                                    const uint32_t aoff = (uint32_t)(((2 * m + oy) * TWP + ox) * 16) >> 4;
+                                    umma_f16_elect(acc0 + m * N, a_base + aoff, DESC_HI, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
+                                    if (nplanes == 2) umma_f16_elect(acc0 + m * N, a_base + (uint32_t)(A_PLANE >> 4) + aoff, DESC_HI, b_lo, DESC_HI, idesc, 1u);
                                 }
-                                first = 0;
                             }
                     }
-                    umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+                    umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
                 }
-                umma_commit(&acc_full[buf]);
+                umma_commit_elect(&acc_full[buf]);
             }
         }
     } else {

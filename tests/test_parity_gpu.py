@@ -105,4 +105,9 @@ def test_batch_and_device_entry_points_match_process(pkg):
     r.process_batch_ptr([f.ctypes.data for f in frames[:3]], [f.ctypes.data for f in frames[1:]], w, h, [0.5] * 3, [o.ctypes.data for o in outs])
     for s, o in zip(singles, outs):
         assert np.array_equal(s, o)
+    # more lanes than pairs, fewer lanes than pairs, timestep edge inside a batch
+    r.set_option("lanes", 3)
+    outs2 = [np.empty_like(frames[0]) for _ in range(3)]
+    r.process_batch_ptr([f.ctypes.data for f in frames[:3]], [f.ctypes.data for f in frames[1:]], w, h, [0.5, 1.0, 0.5], [o.ctypes.data for o in outs2])
+    assert np.array_equal(outs2[0], singles[0]) and np.array_equal(outs2[1], frames[2]) and np.array_equal(outs2[2], singles[2])
     r.close()
