@@ -85,6 +85,10 @@ int rife_b200_set_stream(rife_b200_t* handle, void* cuda_stream);
  * device-resident synthetic data and returns; used by bench.py to time the dominant kernel with its own events. */
 int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
 
+/* Diagnostics: clock64 timeline (64 slots per CTA) of one tcgen05 conv launch; see csrc/tc_conv.cu for the slot map */
+int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, int split, unsigned long long* host_out,
+                                  int max_ctas);
+
 /* Diagnostics: runs ONE convolution layer through the tcgen05 tensor-core kernel and through the fp32 CUDA-core
  * kernel on the same data and returns both results (planar fp32, host memory) so a test can compare them.
  * mode 0: conv3x3 s1 p1 (+bias, + optional residual `res`, + leaky `slope`), in [cin][h][w] -> out [cout][h][w]

@@ -54,6 +54,7 @@ def lib():
 EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
            "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv",
+           "rife_b200_debug_conv_timeline",
            "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
 
 
@@ -151,6 +152,16 @@ def bench_conv(cuda_stream_ptr, cin, cout, h, w, split, iters, gpuid=0):
     rc = lib().rife_b200_bench_conv(gpuid, ctypes.c_void_p(cuda_stream_ptr), cin, cout, h, w, int(split), iters)
     if rc != 0:
         raise RifeError("bench_conv failed: %d" % rc)
+
+
+def debug_conv_timeline(cin, cout, h, w, split=True, max_ctas=148, gpuid=0):
+    buf = np.zeros((max_ctas, 64), np.uint64)
+    L = lib()
+    L.rife_b200_debug_conv_timeline.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_int]
+    rc = L.rife_b200_debug_conv_timeline(gpuid, cin, cout, h, w, int(split), buf.ctypes.data, max_ctas)
+    if rc != 0:
+        raise RifeError("debug_conv_timeline failed: %d" % rc)
+    return buf
 
 
 def launch_count():

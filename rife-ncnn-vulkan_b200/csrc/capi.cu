@@ -296,11 +296,32 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     GUARD_END
 }
 
+extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
+
 extern "C" int rife_b200_set_stream(rife_b200_t* h, void* cuda_stream) {
     GUARD_BEGIN
     if (!h) return RIFE_B200_ERR_ARG;
     h->eng->set_stream((cudaStream_t)cuda_stream);
     return RIFE_B200_OK;
+    GUARD_END
+}
+
+static unsigned long long* g_dbg_dev = nullptr;
+
+// diagnostics: per-CTA clock64 timeline of one tcgen05 conv launch (64 slots per CTA, see tc_conv.cu)
+extern "C" int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, int split, unsigned long long* host_out, int max_ctas) {
+    GUARD_BEGIN
+    if (!host_out || max_ctas <= 0) return RIFE_B200_ERR_ARG;
+    if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
+    size_t bytes = (size_t)max_ctas * 64 * 8;
+    cudaMalloc(&g_dbg_dev, bytes);
+    cudaMemset(g_dbg_dev, 0, bytes);
+    int r = rife_b200_bench_conv(gpuid, nullptr, cin, cout, h, w, split, 3);  // warm (dbg active on every launch; last one kept)
+    cudaDeviceSynchronize();
+    cudaMemcpy(host_out, g_dbg_dev, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(g_dbg_dev);
+    g_dbg_dev = nullptr;
+    return r;
     GUARD_END
 }
 
@@ -338,6 +359,7 @@ extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int c
     a.wpk = c.wpk; a.bias = c.bias; a.out = c.out8; a.out_plane = (size_t)cout * hw; a.slope = 0.2f;
     a.res = cin == cout ? c.in8 : nullptr; a.res_plane = (size_t)cin * hw; a.res_split = split; a.res_mode = cin == cout ? 1 : 0;
     a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = cout; a.split_in = split; a.split_out = split; a.epi = TC_EPI_C8; a.act_mode = 1;
+    a.dbg = g_dbg_dev;
     for (int i = 0; i < iters; i++) {
         int r = launch_tc_conv(a, c.in8, st);
         if (r) return RIFE_B200_ERR_INTERNAL;

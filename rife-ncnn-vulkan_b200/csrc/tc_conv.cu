@@ -106,6 +106,8 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint32_t a_lo, u
         "}\n" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
 }
+#include "tc_mma_issue.inc"
+
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n"
@@ -179,12 +181,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     }
     for (int i = threadIdx.x; i < N; i += NTHREADS) {
         bias_s[i] = a.bias[i];
-        slope_s[i] = (a.act_mode == 2 && i < a.Cout) ? a.prelu[i] : 0.f;
+        slope_s[i] = (a.act_mode == 1 ? a.slope : ((a.act_mode == 2 && i < a.Cout) ? a.prelu[i] : 1.f)) - 1.f;  // stored as slope - 1
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    unsigned long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 64 : nullptr;
+    if (dbg && threadIdx.x == 0) {
+        dbg[0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[60] = gt;
+    }
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -202,6 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     for (int p = 0; p < nplanes; p++)
                         tma_load_3d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc);
                     bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
+                    if (dbg && it < 12) dbg[1 + it] = clock64();
                 }
             }
         }
@@ -225,21 +235,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+                    if (dbg && it < 12 && lane == 0) dbg[16 + it] = clock64();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_base = (st >> 4) | A_LBO;
                     const uint32_t b_base = ((st + nplanes * A_PLANE) >> 4) | B_LBO;
                     const uint32_t nz = kc != 0;
+                    constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
                     if constexpr (TAPS == 9) {
 #pragma unroll
                         for (int tap = 0; tap < 9; tap++) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t b_lo = b_base + (uint32_t)(tap * (2 * N * 16) >> 4);
-#pragma unroll
-                            for (int m = 0; m < MT; m++) {
-                                const uint32_t aoff = (uint32_t)((((2 * m + dy) * TWP + dx) * 16) >> 4);
-                                umma_f16_elect(acc0 + m * N, a_base + aoff, DESC_HI, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
-                                if (nplanes == 2) umma_f16_elect(acc0 + m * N, a_base + (uint32_t)(A_PLANE >> 4) + aoff, DESC_HI, b_lo, DESC_HI, idesc, 1u);
-                            }
+                            const uint32_t a_lo = a_base + (uint32_t)(((dy * TWP + dx) * 16) >> 4);
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
                         }
                     } else {
                         const int par = kc / KCP, py = par >> 1, px = par & 1;
@@ -252,15 +261,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 // even sub-image: single slot = tap d=1 (view offset 1)
                                 const int oy = py ? iy : 1, ox = px ? ix : 1;
                                 const uint32_t b_lo = b_base + (uint32_t)((iy * 2 + ix) * (2 * N * 16) >> 4);
-#pragma unroll
-                                for (int m = 0; m < MT; m++) {
-                                    const uint32_t aoff = (uint32_t)(((2 * m + oy) * TWP + ox) * 16) >> 4;
-                                    umma_f16_elect(acc0 + m * N, a_base + aoff, DESC_HI, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
-                                    if (nplanes == 2) umma_f16_elect(acc0 + m * N, a_base + (uint32_t)(A_PLANE >> 4) + aoff, DESC_HI, b_lo, DESC_HI, idesc, 1u);
-                                }
+                                const uint32_t a_lo = a_base + (uint32_t)(((oy * TWP + ox) * 16) >> 4);
+                                if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
+                                else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
                             }
                     }
                     umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
+                    if (dbg && it < 12 && lane == 0) dbg[32 + it] = clock64();
                 }
                 umma_commit_elect(&acc_full[buf]);
             }
@@ -285,11 +292,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             const int x = x0 + xr;
             const bool xvalid = xr < TVALID && x < a.W;
             if (a.epi == TC_EPI_C8) {
-                uint4 rb[2][2 * G];
+                // v = act(acc + bias + m1*res) + m2*res with per-channel slopes from shared memory: one branch-free body
+                // for every (residual, leaky / PReLU / none) combination keeps the unrolled code small (an earlier, fully
+                // unrolled and flag-branchy version was 215 KB of SASS and instruction-fetch bound).
+                const float m1 = a.res_mode == 1 ? 1.f : 0.f, m2 = a.res_mode == 2 ? 1.f : 0.f;
+                const bool has_res = a.res_mode != 0;
                 auto prefetch = [&](int blk, uint4* dst) {
                     const int m = blk / NCB, cb = blk % NCB;
                     const int y = y0 + 2 * m + yrow;
-                    if (a.res_mode == 0 || !xvalid || y >= a.H) return;
+                    if (!has_res || !xvalid || y >= a.H) return;
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const size_t off = ((size_t)(cb * G + g) * HW + (size_t)y * a.W + x) * 8;
@@ -297,17 +308,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                         if (a.res_split) dst[G + g] = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
                     }
                 };
-                prefetch(0, rb[0]);
-                mbar_wait(&acc_full[buf], aph);
-                tc_fence_after();
-#pragma unroll
-                for (int blk = 0; blk < NBLK; blk++) {
-                    if (blk + 1 < NBLK) prefetch(blk + 1, rb[(blk + 1) & 1]);
-                    const uint4* rcur = rb[blk & 1];
+                auto process = [&](int blk, const uint4* rcur) {
                     const int m = blk / NCB, cb = blk % NCB;
                     const int y = y0 + 2 * m + yrow;
                     const bool valid = xvalid && y < a.H;
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N + cb * CB;
+                    const size_t pix = !a.out_s2d ? (size_t)y * a.W + x : (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
+                    const size_t cg_stride = !a.out_s2d ? HW : (HW >> 2);
+                    const size_t cg_base = !a.out_s2d ? 0 : (size_t)((y & 1) * 2 + (x & 1)) * (a.Cout / 8);
 #pragma unroll
                     for (int c = 0; c < CB / 16; c++) {
                         uint32_t r[16];
@@ -316,57 +324,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                         if (valid) {
 #pragma unroll
                             for (int g2 = 0; g2 < 2; g2++) {
-                                const int gl = c * 2 + g2;           // group inside the block
-                                const int cg = cb * G + gl;          // global 8-channel group
-                                const size_t off = ((size_t)cg * HW + (size_t)y * a.W + x) * 8;
-                                // space-to-depth output (feeds a stride-2 tensor-core conv): [py*2+px][C/8][H/2][W/2][8]
-                                const size_t ooff = !a.out_s2d ? off
-                                    : ((((size_t)((y & 1) * 2 + (x & 1)) * (a.Cout / 8) + cg) * (a.H >> 1) + (y >> 1)) * (size_t)(a.W >> 1) + (x >> 1)) * 8;
-                                float vv[8];
+                                const int gl = c * 2 + g2;   // group inside the block
+                                const int cg = cb * G + gl;  // global 8-channel group
+                                const float4 bA = *reinterpret_cast<const float4*>(bias_s + cg * 8), bB = *reinterpret_cast<const float4*>(bias_s + cg * 8 + 4);
+                                const float4 sA = *reinterpret_cast<const float4*>(slope_s + cg * 8), sB = *reinterpret_cast<const float4*>(slope_s + cg * 8 + 4);
+                                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                                const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};  // slope - 1
+                                float v[8], rr[8];
 #pragma unroll
-                                for (int j = 0; j < 8; j++) vv[j] = __uint_as_float(r[g2 * 8 + j]) + bias_s[cg * 8 + j];
-                                if (a.res_mode != 0) {
-                                    const __half* hh = reinterpret_cast<const __half*>(&rcur[gl]);
-                                    const __half* ll = reinterpret_cast<const __half*>(&rcur[G + gl]);
-                                    float rr[8];
+                                for (int j = 0; j < 8; j++) { v[j] = __uint_as_float(r[g2 * 8 + j]) + bb[j]; rr[j] = 0.f; }
+                                if (has_res) {
+                                    const __half2* hh = reinterpret_cast<const __half2*>(&rcur[gl]);
 #pragma unroll
-                                    for (int j = 0; j < 8; j++) rr[j] = __half2float(hh[j]) + (a.res_split ? __half2float(ll[j]) : 0.f);
-                                    if (a.res_mode == 1) {
+                                    for (int k = 0; k < 4; k++) { float2 f = __half22float2(hh[k]); rr[2 * k] = f.x; rr[2 * k + 1] = f.y; }
+                                    if (a.res_split) {
+                                        const __half2* ll = reinterpret_cast<const __half2*>(&rcur[G + gl]);
 #pragma unroll
-                                        for (int j = 0; j < 8; j++) vv[j] += rr[j];
+                                        for (int k = 0; k < 4; k++) { float2 f = __half22float2(ll[k]); rr[2 * k] += f.x; rr[2 * k + 1] += f.y; }
                                     }
-                                    if (a.act_mode == 1) {
 #pragma unroll
-                                        for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
-                                    } else if (a.act_mode == 2) {
-#pragma unroll
-                                        for (int j = 0; j < 8; j++) vv[j] = vv[j] < 0.f ? vv[j] * slope_s[cg * 8 + j] : vv[j];
-                                    }
-                                    if (a.res_mode == 2) {
-#pragma unroll
-                                        for (int j = 0; j < 8; j++) vv[j] += rr[j];
-                                    }
-                                } else if (a.act_mode == 1) {
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * a.slope;
-                                } else if (a.act_mode == 2) {
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) vv[j] = vv[j] < 0.f ? vv[j] * slope_s[cg * 8 + j] : vv[j];
+                                    for (int j = 0; j < 8; j++) v[j] = fmaf(m1, rr[j], v[j]);
                                 }
-                                __half hi[8];
+                                // leaky / PReLU / identity: v*s for v < 0  ==  v + min(v,0)*(s-1)
 #pragma unroll
-                                for (int j = 0; j < 8; j++) hi[j] = __float2half_rn(vv[j]);
-                                *reinterpret_cast<uint4*>(a.out + ooff) =
-                                    make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+                                for (int j = 0; j < 8; j++) v[j] = fmaf(fminf(v[j], 0.f), ss[j], v[j]);
+                                if (has_res) {
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) v[j] = fmaf(m2, rr[j], v[j]);
+                                }
+                                __half2 h[4];
+#pragma unroll
+                                for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                                const size_t ooff = ((cg_base + cg) * cg_stride + pix) * 8;
+                                *reinterpret_cast<uint4*>(a.out + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                                                                                     *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
                                 if (a.split_out) {
-                                    __half lo[8];
+                                    __half2 l[4];
 #pragma unroll
-                                    for (int j = 0; j < 8; j++) lo[j] = __float2half_rn(vv[j] - __half2float(hi[j]));
-                                    *reinterpret_cast<uint4*>(a.out + a.out_plane + ooff) =
-                                        make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+                                    for (int k = 0; k < 4; k++) {
+                                        float2 f = __half22float2(h[k]);
+                                        l[k] = __floats2half2_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+                                    }
+                                    *reinterpret_cast<uint4*>(a.out + a.out_plane + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                                                                                                       *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
                                 }
                             }
                         }
+                    }
+                };
+                uint4 rb0[2 * G], rb1[2 * G];
+                prefetch(0, rb0);
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
+                if (dbg && warp == 2 && lane == 0 && tcount < 4) dbg[44 + 2 * tcount] = clock64();
+#pragma unroll 1
+                for (int blk = 0; blk < NBLK; blk += 2) {
+                    if (blk + 1 < NBLK) prefetch(blk + 1, rb1);
+                    process(blk, rb0);
+                    if (blk + 1 < NBLK) {
+                        if (blk + 2 < NBLK) prefetch(blk + 2, rb0);
+                        process(blk + 1, rb1);
                     }
                 }
             } else {
@@ -430,12 +447,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
+            if (dbg && warp == 2 && lane == 0 && tcount < 4) dbg[45 + 2 * tcount] = clock64();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[56] = clock64();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

@@ -29,6 +29,7 @@ struct TcConvArgs {
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
+    unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
 };
 
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
