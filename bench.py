@@ -280,7 +280,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
-                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes,
+                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "fused_v46_path": bool(eng.get_option("fast_active")),
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
                 "gflop_per_frame": GFLOP_PER_FRAME[args.workload],
                 "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0,

@@ -70,6 +70,9 @@ int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned ch
  * convolutions with split-precision operands where needed).  Default 1 when the model supports it. */
 /* other keys: "lanes" (1-4 concurrent pairs in flight), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path) */
 int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
+/* reads back "precision", "lanes", "fast" (requested) and "fast_active" (1 when the fused rife-v4.6 path passed its
+ * load-time self-check against the generic executor and is the one process() runs) */
+int rife_b200_get_option(rife_b200_t* handle, const char* key, int* value);
 
 /* packed-weights path for multi-GPU loading without re-reading the model directory on every rank */
 int rife_b200_weights_size(rife_b200_t* handle, size_t* bytes);                 /* after load() on rank 0 */

@@ -35,6 +35,7 @@ def lib():
     L.rife_b200_process_device.argtypes = [vp, vp, vp, ci, ci, cf, vp]
     L.rife_b200_process_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ctypes.POINTER(cf), ctypes.POINTER(vp)]
     L.rife_b200_process_batch_device.argtypes = L.rife_b200_process_batch.argtypes
+    L.rife_b200_get_option.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ci)]
     L.rife_b200_set_option.argtypes = [vp, ctypes.c_char_p, ci]
     L.rife_b200_weights_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     L.rife_b200_weights_export.argtypes = [vp, vp, ctypes.c_size_t]
@@ -52,7 +53,7 @@ def lib():
 
 
 EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
-           "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_weights_size", "rife_b200_weights_export",
+           "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_get_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv",
            "rife_b200_debug_conv_timeline",
            "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
@@ -95,6 +96,11 @@ class RIFE:
 
     def set_option(self, key, value):
         self._check(self._lib.rife_b200_set_option(self._h, key.encode(), int(value)), "set_option(%s)" % key)
+
+    def get_option(self, key):
+        v = ctypes.c_int()
+        self._check(self._lib.rife_b200_get_option(self._h, key.encode(), ctypes.byref(v)), "get_option(%s)" % key)
+        return v.value
 
     def process(self, in0image, in1image, timestep, outimage=None):
         """in0image/in1image: uint8 arrays (h, w, 3), C-contiguous host memory. Returns outimage."""

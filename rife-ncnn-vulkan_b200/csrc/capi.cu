@@ -102,6 +102,13 @@ int rife_b200_set_option(rife_b200_t* h, const char* key, int value) {
     GUARD_END
 }
 
+int rife_b200_get_option(rife_b200_t* h, const char* key, int* value) {
+    GUARD_BEGIN
+    if (!h || !key || !value) return RIFE_B200_ERR_ARG;
+    return map_err(h->eng->get_option(key, value));
+    GUARD_END
+}
+
 int rife_b200_weights_size(rife_b200_t* h, size_t* bytes) {
     GUARD_BEGIN
     if (!h || !bytes) return RIFE_B200_ERR_ARG;

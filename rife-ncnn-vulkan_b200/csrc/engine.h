@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "exec.h"
+#include "fused_v46.h"
 #include "model.h"
 
 namespace rife {
@@ -27,6 +28,7 @@ struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     NetRunner* run[3] = {nullptr, nullptr, nullptr};
+    V46Runner* fast = nullptr;  // hand-scheduled rife-v4.6 path (plain mode, precision tier 1)
     DevBuf pad0[8], pad1[8], ts[2], tsr[2];
     DevBuf flow[4][8], flowr[4][8];
     DevBuf outp[16];
@@ -48,6 +50,7 @@ public:
     int process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out);
     int process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out);
     int set_option(const std::string& key, int value);
+    int get_option(const std::string& key, int* value);
     void set_stream(cudaStream_t s) { std::lock_guard<std::mutex> lk(mu_); user_stream_ = s; use_user_stream_ = s != nullptr; }
     std::string last_error;
 
@@ -57,6 +60,7 @@ private:
     int run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
     int run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st);
     int make_lanes(int n);
+    void setup_fast();      // (re)creates the per-lane fast runners and validates them against the generic executor
     Tensor keep(const Tensor& t, DevBuf& b, cudaStream_t st);  // copy a plan-owned tensor into an engine buffer
 
     int gpuid_;
@@ -64,6 +68,8 @@ private:
     bool loaded_ = false;
     int precision_ = 1;
     bool async_ = false;
+    bool fast_ok_ = false;  // the fused v4.6 path reproduced the generic executor on the self-check
+    int use_fast_ = 1;
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;
     Net nets_[3];           // flownet, contextnet, fusionnet

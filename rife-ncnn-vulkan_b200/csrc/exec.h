@@ -56,6 +56,7 @@ public:
             std::vector<Tensor>& out_tensors, cudaStream_t st, std::string& err);
 
     size_t arena_bytes() const;
+    const DeviceWeights& weights(int layer) const { return (*dwp_)[layer]; }
 
 private:
     struct Step {

@@ -1,0 +1,360 @@
+// fused_v46.cu -- hand-scheduled fast path for the rife-v4.6 IFNet (the BASELINE hot path): the ~50 elementwise
+// graph nodes between the conv stacks (Interp / Crop / BinaryOp / Eltwise / Concat / rife.Warp / Sigmoid, SURVEY.md
+// Appendix B) collapse into four HBM kernels, and every convolution runs on the tcgen05 kernel (tc_conv.cu):
+//   head0   x0 = bilinear(cat(I0, I1, T), 1/8)                                   -> C8 space-to-depth, split fp16
+//   head<S> x  = cat(bilinear(cat(warp(I0,F01), warp(I1,F23), T, M), 1/S), bilinear(F, 1/S) / S)   (S = 4, 2, 1)
+//   update  U = bilinear(d_k, S); F = F + S*U[0:4] (k = 0: F = S*U[0:4]); M = M + U[4]
+//   tail    F3 = F + d3[0:4]; M3 = M + d3[4]; out = warp(I0,F3_01)*sigmoid(M3) + warp(I1,F3_23)*(1 - sigmoid(M3)) -> u8
+// Arithmetic is the generic executor's, operation for operation (same lin_coeff, H pass then V pass, same warp), so the
+// two paths agree to fp32 rounding; Engine::load() additionally checks the fast path against the generic executor on a
+// small random frame pair and silently keeps the generic path when the graph is not the expected one.
+// Reference dataflow: /root/reference/models/rife-v4.6/flownet.param:1-217.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fused_v46.h"
+#include "kernels.h"
+#include "tc_conv.h"
+
+namespace rife {
+
+namespace {
+
+// interp.cpp:54-91 (coefficient in double, rounded to float)
+__device__ __forceinline__ void lin_coeff(int d, int in_n, int out_n, int& s, float& f) {
+    double scale = (double)in_n / out_n;
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= in_n - 1) { sx = in_n - 2; fx = 1.f; }
+    s = sx;
+    f = fx;
+}
+__device__ __forceinline__ float bilerp(const float* __restrict__ p, int w, int sy, int sx, float a0, float a1, float b0, float b1) {
+    const float* r0 = p + (size_t)sy * w + sx;
+    const float* r1 = r0 + w;
+    float row0 = r0[0] * a0 + r0[1] * a1;  // interp.cpp:92-175: horizontal pass, then vertical
+    float row1 = r1[0] * a0 + r1[1] * a1;
+    return row0 * b0 + row1 * b1;
+}
+// src/warp.cpp:96-168 for one pixel: taps and weights (alpha / beta taken after clamping)
+struct WarpTap {
+    int i00, i01, i10, i11;
+    float a, b;
+};
+__device__ __forceinline__ WarpTap warp_tap(int x, int y, float fx, float fy, int w, int h) {
+    float sx = x + fx, sy = y + fy;
+    int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = min(max(x0, 0), w - 1);
+    y0 = min(max(y0, 0), h - 1);
+    x1 = min(max(x1, 0), w - 1);
+    y1 = min(max(y1, 0), h - 1);
+    WarpTap t;
+    t.a = sx - x0;
+    t.b = sy - y0;
+    t.i00 = y0 * w + x0; t.i01 = y0 * w + x1; t.i10 = y1 * w + x0; t.i11 = y1 * w + x1;
+    return t;
+}
+__device__ __forceinline__ float warp_sample(const float* __restrict__ p, const WarpTap& t) {
+    float v4 = p[t.i00] * (1 - t.a) + p[t.i01] * t.a;
+    float v5 = p[t.i10] * (1 - t.a) + p[t.i11] * t.a;
+    return v4 * (1 - t.b) + v5 * t.b;
+}
+__device__ __forceinline__ uint32_t pack2h(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
+
+// writes 16 channel values of output pixel (oy, ox) (image oh x ow) as split fp16 into the space-to-depth C8 tensor
+// [plane][py*2+px][2 groups][oh/2][ow/2][8]
+__device__ __forceinline__ void store_c8_s2d_16(__half* out, const float* v, int oy, int ox, int oh, int ow) {
+    const size_t sub = (size_t)(oh >> 1) * (ow >> 1);
+    const size_t plane = (size_t)16 * oh * ow;
+    const int par = (oy & 1) * 2 + (ox & 1);
+    const size_t pix = (size_t)(oy >> 1) * (ow >> 1) + (ox >> 1);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            hi[j] = __float2half_rn(v[g * 8 + j]);
+            lo[j] = __float2half_rn(v[g * 8 + j] - __half2float(hi[j]));
+        }
+        const size_t off = (((size_t)par * 2 + g) * sub + pix) * 8;
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(pack2h(hi[0], hi[1]), pack2h(hi[2], hi[3]), pack2h(hi[4], hi[5]), pack2h(hi[6], hi[7]));
+        *reinterpret_cast<uint4*>(out + plane + off) = make_uint4(pack2h(lo[0], lo[1]), pack2h(lo[2], lo[3]), pack2h(lo[4], lo[5]), pack2h(lo[6], lo[7]));
+    }
+}
+
+// x0 = Interp(cat(I0, I1, T), 1/8): flownet.param:9-10
+__global__ void head0_kernel(const float* __restrict__ I0, const float* __restrict__ I1, float t, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    if (ox >= ow) return;
+    int sx, sy;
+    float fx, fy;
+    lin_coeff(ox, wp, ow, sx, fx);
+    lin_coeff(oy, hp, oh, sy, fy);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const size_t plane = (size_t)hp * wp;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        v[c] = bilerp(I0 + c * plane, wp, sy, sx, a0, a1, b0, b1);
+        v[3 + c] = bilerp(I1 + c * plane, wp, sy, sx, a0, a1, b0, b1);
+    }
+    v[6] = (t * a0 + t * a1) * b0 + (t * a0 + t * a1) * b1;  // the timestep plane goes through the same resize arithmetic
+#pragma unroll
+    for (int c = 7; c < 16; c++) v[c] = 0.f;
+    store_c8_s2d_16(out, v, oy, ox, oh, ow);
+}
+
+// block head for k >= 1: flownet.param:50-62 (S = 4), :106-115 (2), :158-165 (1)
+template <int S>
+__global__ void head_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M, float t,
+                            int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    if (ox >= ow) return;
+    const size_t plane = (size_t)hp * wp;
+    float v[16];
+    // 8-channel vector cat(W0, W1, T, M) and the 4 flow channels at one full-resolution pixel
+    auto at = [&](int y, int x, float* e) {
+        const size_t pi = (size_t)y * wp + x;
+        const float f0 = F[pi], f1 = F[plane + pi], f2 = F[2 * plane + pi], f3 = F[3 * plane + pi];
+        WarpTap t0 = warp_tap(x, y, f0, f1, wp, hp);
+        WarpTap t1 = warp_tap(x, y, f2, f3, wp, hp);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            e[c] = warp_sample(I0 + c * plane, t0);
+            e[3 + c] = warp_sample(I1 + c * plane, t1);
+        }
+        e[6] = t;
+        e[7] = M[pi];
+        e[8] = f0; e[9] = f1; e[10] = f2; e[11] = f3;
+    };
+    if (S == 1) {
+        // Interp at identical size returns its input untouched (interp.cpp), then Concat
+        float e[12];
+        at(oy, ox, e);
+#pragma unroll
+        for (int c = 0; c < 12; c++) v[c] = e[c];
+    } else {
+        int sx, sy;
+        float fx, fy;
+        lin_coeff(ox, wp, ow, sx, fx);
+        lin_coeff(oy, hp, oh, sy, fy);
+        const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+        float e00[12], e01[12], e10[12], e11[12];
+        at(sy, sx, e00);
+        at(sy, sx + 1, e01);
+        at(sy + 1, sx, e10);
+        at(sy + 1, sx + 1, e11);
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            float row0 = e00[c] * a0 + e01[c] * a1;
+            float row1 = e10[c] * a0 + e11[c] * a1;
+            v[c] = row0 * b0 + row1 * b1;
+        }
+#pragma unroll
+        for (int c = 8; c < 12; c++) v[c] = v[c] / (float)S;  // BinaryOp div by the scale (flownet.param div_17 / div_37)
+    }
+#pragma unroll
+    for (int c = 12; c < 16; c++) v[c] = 0.f;
+    store_c8_s2d_16(out, v, oy, ox, oh, ow);
+}
+
+// flow / mask update after block k: flownet.param:47-50,58 (k = 0), :99-105 (k = 1), :152-158 (k = 2)
+template <int S, bool FIRST>
+__global__ void update_kernel(const float* __restrict__ d, int dh, int dw, float* __restrict__ F, float* __restrict__ M, int hp, int wp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wp) return;
+    int sx, sy;
+    float fx, fy;
+    lin_coeff(x, dw, wp, sx, fx);
+    lin_coeff(y, dh, hp, sy, fy);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const size_t dplane = (size_t)dh * dw, plane = (size_t)hp * wp, pi = (size_t)y * wp + x;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float u = bilerp(d + c * dplane, dw, sy, sx, a0, a1, b0, b1);
+        if (FIRST) F[c * plane + pi] = u * (float)S;                         // BinaryOp mul by scalar
+        else F[c * plane + pi] = F[c * plane + pi] * 1.f + u * (float)S;     // Eltwise SUM, coeffs {1, S}
+    }
+    float um = bilerp(d + 4 * dplane, dw, sy, sx, a0, a1, b0, b1);
+    if (FIRST) M[pi] = um;
+    else M[pi] = M[pi] + um;
+}
+
+// last update + blend + rife_postproc: flownet.param:202-217, src/rife.cpp:4375-4398, mat_pixel.cpp:158
+__global__ void tail_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M,
+                            const float* __restrict__ d3, int hp, int wp, uint8_t* __restrict__ rgb, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    // the reference CPU path reads the first w*h floats of each padded output channel contiguously (rife.cpp:4375-4387)
+    const size_t idx = (size_t)y * w + x;
+    const int Y = (int)(idx / wp), X = (int)(idx - (size_t)Y * wp);
+    const size_t plane = (size_t)hp * wp, pi = (size_t)Y * wp + X;
+    const float f0 = F[pi] + d3[pi], f1 = F[plane + pi] + d3[plane + pi];
+    const float f2 = F[2 * plane + pi] + d3[2 * plane + pi], f3 = F[3 * plane + pi] + d3[3 * plane + pi];
+    float m = M[pi] + d3[4 * plane + pi];
+    m = fminf(m, 88.3762626647949f);
+    m = fmaxf(m, -88.3762626647949f);
+    m = 1.f / (1.f + expf(-m));   // sigmoid.cpp:42-44
+    const float om = 1.f - m;     // BinaryOp rsub
+    WarpTap t0 = warp_tap(X, Y, f0, f1, wp, hp);
+    WarpTap t1 = warp_tap(X, Y, f2, f3, wp, hp);
+    uint8_t* o = rgb + idx * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float w0 = warp_sample(I0 + c * plane, t0) * m;
+        float w1 = warp_sample(I1 + c * plane, t1) * om;
+        float v = (w0 + w1) * 255.f + 0.5f;
+        int iv = (int)v;
+        o[c] = (uint8_t)min(max(iv, 0), 255);
+    }
+}
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+int V46Runner::init(const Net* net, const NetRunner* weights, std::string& err) {
+    ok_ = false;
+    net_ = net;
+    wr_ = weights;
+    conv_.clear();
+    for (size_t i = 0; i < net->layers.size(); i++) {
+        const Layer& L = net->layers[i];
+        if (L.type == "Convolution" || L.type == "Deconvolution") conv_.push_back((int)i);
+    }
+    if (conv_.size() != 44) { err = "not a 4-block IFNet"; return -1; }
+    static const int cw[4] = {192, 128, 96, 64};
+    for (int k = 0; k < 4; k++) {
+        for (int j = 0; j < 11; j++) {
+            const Layer& L = net->layers[conv_[k * 11 + j]];
+            const DeviceWeights& W = weights->weights(conv_[k * 11 + j]);
+            bool isdeconv = j == 10;
+            if ((L.type == "Deconvolution") != isdeconv || !W.wpk) { err = "layer order / tensor-core eligibility mismatch at " + L.name; return -1; }
+            int cout = L.geti(0, 0);
+            int want = j == 0 ? cw[k] / 2 : (j == 10 ? 24 : cw[k]);
+            int wcin = j == 0 ? (k == 0 ? 7 : 12) : (j == 1 ? cw[k] / 2 : cw[k]);
+            if (cout != want || W.cin != wcin || (j < 2) != (W.tc_s2 != 0)) { err = "unexpected shape at " + L.name; return -1; }
+        }
+    }
+    // leaky slope of the residual blocks: the ReLU layers of the graph
+    slope_ = -1.f;
+    for (const Layer& L : net->layers)
+        if (L.type == "ReLU") { slope_ = L.getf(0, 0.f); break; }
+    if (slope_ < 0.f || net->find_blob("flow3") < 0 || net->find_blob("out0") < 0) { err = "no ReLU / flow3 / out0 in graph"; return -1; }
+    ok_ = true;
+    return 0;
+}
+
+V46Runner::~V46Runner() {
+    for (void* p : bufs_) cudaFree(p);
+}
+
+int V46Runner::ensure(int w, int h, std::string& err) {
+    const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
+    if (wp == wp_ && hp == hp_) return 0;
+    for (void* p : bufs_) cudaFree(p);
+    bufs_.clear();
+    auto alloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        bufs_.push_back(p);
+        return p;
+    };
+    const size_t plane = (size_t)wp * hp;
+    I0_ = (float*)alloc(3 * plane * 4);
+    I1_ = (float*)alloc(3 * plane * 4);
+    F_ = (float*)alloc(4 * plane * 4);
+    M_ = (float*)alloc(plane * 4);
+    static const int S[4] = {8, 4, 2, 1};
+    bool fail = !I0_ || !I1_ || !F_ || !M_;
+    for (int k = 0; k < 4; k++) {
+        const size_t hk = hp / S[k], wk = wp / S[k];
+        const int c = 192 >> 0;
+        (void)c;
+        static const int cw[4] = {192, 128, 96, 64};
+        d_[k] = (float*)alloc(6 * hk * wk * 4);
+        x_[k] = (__half*)alloc((size_t)16 * hk * wk * 2 * 2);                         // head, C8 s2d, hi+lo
+        y0_[k] = (__half*)alloc((size_t)(cw[k] / 2) * (hk / 2) * (wk / 2) * 2 * 2);   // conv0 out, C8 s2d
+        a_[k] = (__half*)alloc((size_t)cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain ping
+        b_[k] = (__half*)alloc((size_t)cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain pong
+        fail = fail || !d_[k] || !x_[k] || !y0_[k] || !a_[k] || !b_[k];
+    }
+    if (fail) { err = "cudaMalloc failed"; wp_ = hp_ = 0; return -2; }
+    wp_ = wp;
+    hp_ = hp;
+    return 0;
+}
+
+int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, cudaStream_t st) {
+    const Layer& L = net_->layers[li];
+    const DeviceWeights& W = wr_->weights(li);
+    TcConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.wpk = (const __half*)W.wpk;
+    a.bias = W.biasN;
+    a.H = oh; a.W = ow; a.Cin = W.cinp; a.Cout = L.geti(0, 0); a.N = W.tcN;
+    a.split_in = 1;
+    a.s2 = W.tc_s2;
+    a.num_sms = wr_->num_sms;
+    if (L.type == "Convolution") {
+        a.epi = TC_EPI_C8;
+        a.out = out;
+        a.out_plane = (size_t)a.Cout * oh * ow;
+        a.split_out = 1;
+        a.out_s2d = out_s2d;
+        a.act_mode = 1;
+        a.slope = slope_;
+        if (L.geti(9, 0) == 2) { const ParamVal* ap = L.get(10); a.slope = ap && !ap->af.empty() ? ap->af[0] : 0.f; }
+        if (res) { a.res = res; a.res_plane = a.out_plane; a.res_split = 1; a.res_mode = 1; }
+    } else {
+        a.epi = TC_EPI_DECONV;
+        a.out_f32 = out_f32;
+        a.ocs = W.ocs;
+        a.ps = 2;
+    }
+    return launch_tc_conv(a, in, st);
+}
+
+int V46Runner::run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err) {
+    if (!ok_) { err = "fast path not initialised"; return -1; }
+    if (ensure(w, h, err)) return -2;
+    const int wp = wp_, hp = hp_;
+    static const int S[4] = {8, 4, 2, 1};
+    launch_preproc(d_in0, w, h, I0_, wp, hp, 0, st);
+    launch_preproc(d_in1, w, h, I1_, wp, hp, 0, st);
+    for (int k = 0; k < 4; k++) {
+        const int hk = hp / S[k], wk = wp / S[k];
+        dim3 g(cdiv(wk, 128), hk);
+        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(I0_, I1_, t, hp, wp, hk, wk, x_[0]);
+        else if (k == 1) head_kernel<4><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[1]);
+        else if (k == 2) head_kernel<2><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[2]);
+        else head_kernel<1><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[3]);
+        g_launch_count++;
+        const int* L = &conv_[k * 11];
+        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, st);   // 3x3 s2, leaky
+        r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, st);     // 3x3 s2, leaky
+        __half* cur = a_[k];
+        __half* nxt = b_[k];
+        for (int j = 0; j < 8; j++) {                                                  // y = leaky(conv(y) + y)
+            r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, st);
+            __half* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, st);       // deconv + PixelShuffle -> flow<k>
+        if (r) { err = "tensor-core conv launch failed in block " + std::to_string(k); return -3; }
+        dim3 gf(cdiv(wp, 128), hp);
+        if (k == 0) update_kernel<8, true><<<gf, 128, 0, st>>>(d_[0], hk, wk, F_, M_, hp, wp);
+        else if (k == 1) update_kernel<4, false><<<gf, 128, 0, st>>>(d_[1], hk, wk, F_, M_, hp, wp);
+        else if (k == 2) update_kernel<2, false><<<gf, 128, 0, st>>>(d_[2], hk, wk, F_, M_, hp, wp);
+        if (k < 3) g_launch_count++;
+    }
+    tail_kernel<<<dim3(cdiv(w, 128), h), 128, 0, st>>>(I0_, I1_, F_, M_, d_[3], hp, wp, d_out, w, h);
+    g_launch_count++;
+    return 0;
+}
+
+}  // namespace rife

@@ -1,0 +1,37 @@
+// fused_v46.h -- hand-scheduled fast path for the rife-v4.6 IFNet (see fused_v46.cu)
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "exec.h"
+#include "model.h"
+
+namespace rife {
+
+class V46Runner {
+public:
+    ~V46Runner();
+    // `weights` = the NetRunner that owns the packed tensor-core weights of `net` on this device
+    int init(const Net* net, const NetRunner* weights, std::string& err);
+    bool ok() const { return ok_; }
+    int run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err);
+
+private:
+    int ensure(int w, int h, std::string& err);
+    int conv(int layer, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, cudaStream_t st);
+    const Net* net_ = nullptr;
+    const NetRunner* wr_ = nullptr;
+    bool ok_ = false;
+    float slope_ = 0.2f;
+    std::vector<int> conv_;  // the 44 conv / deconv layer indices in graph order
+    int wp_ = 0, hp_ = 0;
+    std::vector<void*> bufs_;
+    float *I0_ = nullptr, *I1_ = nullptr, *F_ = nullptr, *M_ = nullptr, *d_[4] = {};
+    __half *x_[4] = {}, *y0_[4] = {}, *a_[4] = {}, *b_[4] = {};
+};
+
+}  // namespace rife

@@ -28,7 +28,7 @@ namespace {
 
 constexpr int TWP = 64;        // tile width incl. 1-pixel halo left and right -> 62 valid output columns
 constexpr int TVALID = TWP - 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     }
@@ -277,9 +277,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         // Per tile the accumulators are drained in NBLK blocks of CB channels.  The residual (16 B per 8-channel group
         // and plane) for block b+1 is fetched into registers while block b is converted and stored, and the fetch for
         // the first block is issued before waiting for the MMAs, so global-memory latency overlaps the tensor work.
-        constexpr int CB = (N % 64 == 0) ? 64 : ((N % 48 == 0) ? 48 : 32);
+        constexpr int CB = (N % 32 == 0) ? 32 : ((N % 48 == 0) ? 48 : 16);
         constexpr int NCB = N / CB, NBLK = MT * NCB, G = CB / 8;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate channel blocks
         const int p = q * 32 + lane;  // flattened position inside an accumulator
         const int xr = p & (TWP - 1), yrow = p >> 6;
         uint32_t tcount = 0;
@@ -373,17 +374,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     }
                 };
                 uint4 rb0[2 * G], rb1[2 * G];
-                prefetch(0, rb0);
+                // this warp's blocks: ehalf, ehalf + 2, ehalf + 4, ...
+                if (ehalf < NBLK) prefetch(ehalf, rb0);
                 mbar_wait(&acc_full[buf], aph);
                 tc_fence_after();
                 if (dbg && warp == 2 && lane == 0 && tcount < 4) dbg[44 + 2 * tcount] = clock64();
 #pragma unroll 1
-                for (int blk = 0; blk < NBLK; blk += 2) {
-                    if (blk + 1 < NBLK) prefetch(blk + 1, rb1);
+                for (int blk = ehalf; blk < NBLK; blk += 4) {
+                    if (blk + 2 < NBLK) prefetch(blk + 2, rb1);
                     process(blk, rb0);
-                    if (blk + 1 < NBLK) {
-                        if (blk + 2 < NBLK) prefetch(blk + 2, rb0);
-                        process(blk + 1, rb1);
+                    if (blk + 2 < NBLK) {
+                        if (blk + 4 < NBLK) prefetch(blk + 4, rb0);
+                        process(blk + 2, rb1);
                     }
                 }
             } else {
@@ -397,47 +399,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 const int r_ = a.ps;
                 const int OH = a.H * 2 * r_, OW = a.W * 2 * r_;
 #pragma unroll 1
-                for (int m = 0; m < MT; m++) {
+                for (int m = ehalf; m < MT; m += 2) {
                     const int y = y0 + 2 * m + yrow;
                     const bool valid = xvalid && y < a.H;
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N;
-                    float v[N];
+                    constexpr int OCS = N / 4, NH = N / 2;
+                    // the two output-row parities are independent halves of the columns: halves the live registers
 #pragma unroll
-                    for (int c0 = 0; c0 < N; c0 += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(trow + c0, r);
-                        tmem_ld_wait();
+                    for (int py = 0; py < 2; py++) {
+                        float v[NH];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            float val = __uint_as_float(r[j]) + bias_s[c0 + j];
-                            if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
-                            v[c0 + j] = val;
+                        for (int c0 = 0; c0 < NH; c0 += 16) {
+                            uint32_t r[16];
+                            tmem_ld16(trow + py * NH + c0, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                float val = __uint_as_float(r[j]) + bias_s[py * NH + c0 + j];
+                                if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
+                                v[c0 + j] = val;
+                            }
                         }
-                    }
-                    if (!valid) continue;
-                    constexpr int OCS = N / 4;
-                    if (r_ == 2) {
+                        if (!valid) continue;
+                        if (r_ == 2) {
 #pragma unroll
-                        for (int oc4 = 0; oc4 < OCS / 4; oc4++) {   // oc4 = qq
-                            if (oc4 * 4 >= a.Cout) break;
+                            for (int oc4 = 0; oc4 < OCS / 4; oc4++) {  // oc4 = qq
+                                if (oc4 * 4 >= a.Cout) break;
 #pragma unroll
-                            for (int sh = 0; sh < 2; sh++)
-#pragma unroll
-                                for (int py = 0; py < 2; py++) {
+                                for (int sh = 0; sh < 2; sh++) {
                                     const int o0 = oc4 * 4 + sh * 2;  // oc for sw = 0
-                                    float4 w4 = make_float4(v[(py * 2 + 0) * OCS + o0], v[(py * 2 + 0) * OCS + o0 + 1],
-                                                            v[(py * 2 + 1) * OCS + o0], v[(py * 2 + 1) * OCS + o0 + 1]);
+                                    float4 w4 = make_float4(v[o0], v[o0 + 1], v[OCS + o0], v[OCS + o0 + 1]);  // px = 0 | px = 1
                                     const int oy = (2 * y + py) * 2 + sh;
                                     *reinterpret_cast<float4*>(a.out_f32 + ((size_t)oc4 * OH + oy) * OW + 4 * x) = w4;
                                 }
-                        }
-                    } else {
+                            }
+                        } else {
 #pragma unroll
-                        for (int oc = 0; oc < OCS; oc++) {
-                            if (oc >= a.Cout) break;
-#pragma unroll
-                            for (int py = 0; py < 2; py++) {
-                                float2 w2 = make_float2(v[(py * 2 + 0) * OCS + oc], v[(py * 2 + 1) * OCS + oc]);
+                            for (int oc = 0; oc < OCS; oc++) {
+                                if (oc >= a.Cout) break;
+                                float2 w2 = make_float2(v[oc], v[OCS + oc]);
                                 *reinterpret_cast<float2*>(a.out_f32 + ((size_t)oc * OH + 2 * y + py) * OW + 2 * x) = w2;
                             }
                         }

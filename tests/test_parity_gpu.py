@@ -111,3 +111,26 @@ def test_batch_and_device_entry_points_match_process(pkg):
     r.process_batch_ptr([f.ctypes.data for f in frames[:3]], [f.ctypes.data for f in frames[1:]], w, h, [0.5, 1.0, 0.5], [o.ctypes.data for o in outs2])
     assert np.array_equal(outs2[0], singles[0]) and np.array_equal(outs2[1], frames[2]) and np.array_equal(outs2[2], singles[2])
     r.close()
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (640, 360), (100, 70), (1920, 1080)])
+def test_v46_fused_fast_path(pkg, w, h):
+    """The hand-scheduled rife-v4.6 path (fused head / update / tail kernels + tcgen05 convs): active after its
+    load-time self-check, equal to the generic executor up to fp32 rounding, and within tolerance of the oracle."""
+    _need("rife-v4.6")
+    a, b = parity.synth.pair(w, h)
+    v2, v4 = pkg.family_flags("rife-v4.6")
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir("rife-v4.6"))
+    assert r.get_option("fast_active") == 1
+    fast = r.process(a, b, 0.5)
+    r.set_option("fast", 0)
+    assert r.get_option("fast_active") == 0
+    generic = r.process(a, b, 0.5)
+    r.close()
+    d = parity.compare(fast, generic)
+    assert d["max_abs_diff"] <= 1 and d["share_ne"] < 5e-3, d
+    if w * h <= 640 * 360:
+        ref, _ = parity.run_oracle("rife-v4.6", a, b, 0.5)
+        res = parity.compare(fast, ref)
+        assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
