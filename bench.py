@@ -160,18 +160,15 @@ def main():
     eng = pkg.RIFE(local, False, False, args.workload == "4k", 1, v2, v4)
     # weights: rank 0 reads the model directory, everyone else receives the packed blob over NCCL (NVLink)
     if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "rife-ncnn-vulkan_b200"))
+        import dist_util
+        blob = None
         if rank == 0:
             eng.load(md)
-            blob = torch.from_numpy(eng.export_weights()).cuda()
-            n = torch.tensor([blob.numel()], dtype=torch.int64, device="cuda")
-        else:
-            n = torch.zeros(1, dtype=torch.int64, device="cuda")
-        dist.broadcast(n, 0)
+            blob = eng.export_weights()
+        blob = dist_util.broadcast_blob(blob, dist, device=torch.device("cuda", local))
         if rank != 0:
-            blob = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(blob, 0)
-        if rank != 0:
-            eng.load_packed(blob.cpu().numpy())
+            eng.load_packed(blob)
     else:
         eng.load(md)
     eng.set_option("precision", args.precision)
