@@ -129,6 +129,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
+    ap.add_argument("--tta", action="store_true")
+    ap.add_argument("--tta-temporal", action="store_true")
+    ap.add_argument("--timestep", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -153,11 +157,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w, h, desc = WORKLOADS[args.workload]
-    md = parity.model_dir(MODEL)
+    md = parity.model_dir(args.model)
     if md is None:
-        raise SystemExit("model %s not found (oracle/_ref/models or tests/models)" % MODEL)
-    v2, v4 = pkg.family_flags(MODEL)
-    eng = pkg.RIFE(local, False, False, args.workload == "4k", 1, v2, v4)
+        raise SystemExit("model %s not found (oracle/_ref/models or tests/models)" % args.model)
+    v2, v4 = pkg.family_flags(args.model)
+    eng = pkg.RIFE(local, args.tta, args.tta_temporal, args.workload == "4k" and v4, 1, v2, v4)
     # weights: rank 0 reads the model directory, everyone else receives the packed blob over NCCL (NVLink)
     if world > 1:
         sys.path.insert(0, os.path.join(ROOT, "rife-ncnn-vulkan_b200"))
@@ -192,7 +196,7 @@ def main():
     d_out = [t.data_ptr() for t in out_dev]
 
     def step_device():
-        eng.process_batch_ptr(d_in0, d_in1, w, h, [0.5] * PAIRS_PER_STEP, d_out, device=True)
+        eng.process_batch_ptr(d_in0, d_in1, w, h, [args.timestep] * PAIRS_PER_STEP, d_out, device=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,7 +232,7 @@ def main():
     in0 = [t.data_ptr() for t in host[:PAIRS_PER_STEP]]
     in1 = [t.data_ptr() for t in host[1:PAIRS_PER_STEP + 1]]
     outp = [t.data_ptr() for t in out_host]
-    ts = [0.5] * PAIRS_PER_STEP
+    ts = [args.timestep] * PAIRS_PER_STEP
     for _ in range(2):
         eng.process_batch_ptr(in0, in1, w, h, ts, outp)
     barrier()
@@ -261,26 +265,29 @@ def main():
     k_ms = e0.elapsed_time(e1) / iters
     flop = 2.0 * 9 * 64 * 64 * ch * cw  # algorithmic FLOPs of the layer; the hi+lo split issues 2x this on the tensor pipe
     achieved = flop / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md)
+    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
                 "kernel": "tc_conv3x3_kernel<64,4,3> %dx%d" % (cw, ch), "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
                 "tensor_issue_multiplier": 2 if split else 1}
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.model == MODEL and not (args.tta or args.tta_temporal):
             try:
                 cpu = cpu_reference_fps(args.workload, 2 if args.workload == "1080p" else 1)
             except Exception as e:  # the oracle binary did not travel / wrong ISA: report, do not fake
                 cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
         nb = w * h * 3
-        line = {"metric": "interpolated frames/sec (rife-v4.6)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": "interpolated frames/sec (%s)" % args.model, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
-                "config": {"workload": desc, "timestep": 0.5, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "fused_v46_path": bool(eng.get_option("fast_active")),
+                "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
+                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "fused_v46_path": bool(eng.get_option("fast_active")),
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
-                "gflop_per_frame": GFLOP_PER_FRAME[args.workload],
-                "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0,
+                "gflop_per_frame": GFLOP_PER_FRAME[args.workload] if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
+                "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0 if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": 2 * nb * PAIRS_PER_STEP, "d2h_bytes_per_step": nb * PAIRS_PER_STEP},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "out_checksum": checksum}
         print(json.dumps(line))

@@ -1,0 +1,10 @@
+"""Profiling target: the dominant tcgen05 conv (64->64 at quarter resolution of 1080p / 4K) launched alone."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as g
+pkg = g.load_package()
+h, w = (272, 480) if len(sys.argv) < 2 or sys.argv[1] == "1080p" else (544, 960)
+s = torch.cuda.Stream()
+pkg.bench_conv(s.cuda_stream, 64, 64, h, w, 1, 4)
+torch.cuda.synchronize()

@@ -1,28 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_tc_conv_gpu.py -m gpu -q -x 2>&1 | tail -25) > gpurun_out/tc_conv_tests.txt
-tail -4 gpurun_out/tc_conv_tests.txt
-python - <<'PY' > gpurun_out/timeline.txt 2>&1
-import numpy as np, __graft_entry__ as g
-pkg = g.load_package()
-for (c, h, w) in [(64, 272, 480), (128, 68, 120)]:
-    t = pkg.debug_conv_timeline(c, c, h, w, True)
-    for cta in (0, 100):
-        r = t[cta].astype(np.int64)
-        if r[0] == 0: continue
-        b = r[0]
-        f = lambda a: [int(x - b) if x else -1 for x in a]
-        print("c=%d %dx%d cta %d: prod issue" % (c, w, h, cta), f(r[1:13]))
-        print("   mma full seen", f(r[16:28]))
-        print("   mma committed", f(r[32:44]))
-        print("   epi [full,done]x4", f(r[44:52]), "end", int(r[56] - b))
-PY
-cat gpurun_out/timeline.txt
-(timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -q 2>&1 | tail -10) > gpurun_out/parity_tests.txt
-tail -4 gpurun_out/parity_tests.txt
-for lanes in 1 2; do
-(timeout 300 python bench.py --steps 5 --warmup 3 --lanes $lanes --no-cpu-baseline 2>&1 | tail -2) > gpurun_out/bench_1080p_l$lanes.txt
-cut -c1-420 gpurun_out/bench_1080p_l$lanes.txt; grep -o '"roofline.*us_per_launch[^,]*' gpurun_out/bench_1080p_l$lanes.txt
-done
-(timeout 300 python bench.py --steps 5 --warmup 3 --workload 4k --no-cpu-baseline 2>&1 | tail -3) > gpurun_out/bench_4k.txt
-cut -c1-420 gpurun_out/bench_4k.txt; grep -o '"roofline.*us_per_launch[^,]*' gpurun_out/bench_4k.txt
+# (1) launch list of the fused path: 3 frames at 1080p; the last frame's launches are the steady state
+(timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_1080p_fused.csv python tools/profile_frame.py 1080p > gpurun_out/ncu_frame_stdout.txt 2>&1)
+wc -l gpurun_out/launches_1080p_fused.csv
+# (2) full capture of the dominant tensor-core kernel, alone
+(timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_1080p python tools/profile_tc.py 1080p > gpurun_out/ncu_tc_stdout.txt 2>&1)
+(timeout 300 ncu --set full --clock-control none -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_4k python tools/profile_tc.py 4k >> gpurun_out/ncu_tc_stdout.txt 2>&1)
+# (3) full capture of the HBM kernels of the last frame (head x4, update x3, tail, preproc x2 = 10 per frame; skip 2 frames + self-check)
+(timeout 400 ncu --set full --clock-control none -k regex:"head|update_kernel|tail_kernel|preproc" -s 20 -c 10 -o gpurun_out/prof_hbm_1080p python tools/profile_frame.py 1080p > gpurun_out/ncu_hbm_stdout.txt 2>&1)
+ls -la gpurun_out | head -30
