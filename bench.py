@@ -31,7 +31,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {"1080p": (1920, 1080, "rife-v4.6 1920x1080 synthetic frame-pair stream (BASELINE configs[1])"),
              "4k": (3840, 2160, "rife-v4.6 3840x2160 UHD-flag stream (BASELINE configs[2]; -u is a no-op for v4 nets)")}
 GFLOP_PER_FRAME = {"1080p": 175.2, "4k": 701.0}
-PAIRS_PER_STEP = int(os.environ.get("RIFE_BENCH_PAIRS", "8"))  # profiling runs shrink the step
+PAIRS_PER_STEP = int(os.environ.get("RIFE_BENCH_PAIRS", "32"))  # profiling runs shrink the step
+DISTINCT_FRAMES = 9  # consecutive frames of the synthetic stream; pairs cycle through them
 MODEL = "rife-v4.6"
 
 
@@ -44,32 +45,66 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML in-process, every 5 ms;
+    falls back to nvidia-smi when pynvml is unavailable)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, idx):
         super().__init__(daemon=True)
-        self.idx, self.rows, self.stop_flag = idx, [], False
+        self.idx, self.sm, self.mx, self.reasons, self.stop_flag = idx, [], None, set(), False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(idx))
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(idx):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            parts = [p for p in vis.split(",") if p.strip()]
+            if idx < len(parts) and parts[idx].strip().isdigit():
+                return int(parts[idx])
+        return idx
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nvml:
+                    self.sm.append(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        r = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    time.sleep(0.005)
+                else:
+                    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                    if o:
+                        r = [x.strip() for x in o.split(",")]
+                        if r[0].isdigit():
+                            self.sm.append(int(r[0]))
+                        if r[1].isdigit():
+                            self.mx = int(r[1])
+                        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                            if v.lower().startswith("active"):
+                                self.reasons.add(name)
+                    time.sleep(0.1)
             except Exception:
-                pass
-            time.sleep(0.2)
+                time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def cpu_reference_fps(workload, frames, threads=None, warmup=1):
@@ -128,7 +163,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=3)
     ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
     ap.add_argument("--tta", action="store_true")
     ap.add_argument("--tta-temporal", action="store_true")
@@ -179,7 +214,7 @@ def main():
     eng.set_option("lanes", args.lanes)
 
     # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
-    nframes = PAIRS_PER_STEP + 1
+    nframes = min(PAIRS_PER_STEP, DISTINCT_FRAMES - 1) + 1
     frames = [parity.synth.frame(k, w, h, seed=rank) for k in range(nframes)]
     host = [torch.from_numpy(f).pin_memory() for f in frames]
     dev = [t.cuda(non_blocking=True) for t in host]
@@ -191,8 +226,8 @@ def main():
     eng.set_option("async", 1)
     torch.cuda.synchronize()
 
-    d_in0 = [dev[i].data_ptr() for i in range(PAIRS_PER_STEP)]
-    d_in1 = [dev[i + 1].data_ptr() for i in range(PAIRS_PER_STEP)]
+    d_in0 = [dev[i % (nframes - 1)].data_ptr() for i in range(PAIRS_PER_STEP)]
+    d_in1 = [dev[i % (nframes - 1) + 1].data_ptr() for i in range(PAIRS_PER_STEP)]
     d_out = [t.data_ptr() for t in out_dev]
 
     def step_device():
@@ -229,8 +264,8 @@ def main():
     # e2e: host buffers through the batch call (H2D + compute + D2H pipelined inside the library)
     eng.set_stream(0)
     eng.set_option("async", 0)
-    in0 = [t.data_ptr() for t in host[:PAIRS_PER_STEP]]
-    in1 = [t.data_ptr() for t in host[1:PAIRS_PER_STEP + 1]]
+    in0 = [host[i % (nframes - 1)].data_ptr() for i in range(PAIRS_PER_STEP)]
+    in1 = [host[i % (nframes - 1) + 1].data_ptr() for i in range(PAIRS_PER_STEP)]
     outp = [t.data_ptr() for t in out_host]
     ts = [args.timestep] * PAIRS_PER_STEP
     for _ in range(2):

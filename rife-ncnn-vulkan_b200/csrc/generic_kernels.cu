@@ -133,10 +133,13 @@ template <int K, int S, int OCT, int ICC>
 static void launch_conv_t(const ConvArgs& a, cudaStream_t st) {
     constexpr int IW_T = (TW - 1) * S + K, IH_T = (TH - 1) * S + K, IW_P = IW_T | 1;
     size_t smem = sizeof(float) * (ICC * IH_T * IW_P + ICC * K * K * OCT);
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: one process may drive several GPUs (src/main.cpp -g 0,1,...)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaFuncSetAttribute(conv_direct_kernel<K, S, OCT, ICC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev] = true;
     }
     int tiles = ((a.DW + TW - 1) / TW) * ((a.DH + TH - 1) / TH);
     int octiles = (a.Cout + OCT - 1) / OCT;  // weights are padded to ocpad (multiple of 64), so partial tiles read zeros

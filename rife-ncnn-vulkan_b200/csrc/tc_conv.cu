@@ -486,10 +486,14 @@ static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st)
     const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
     const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256 + 2 * N * sizeof(float);
     if (smem > 227 * 1024) return -2;
-    static size_t configured = 0;
-    if (smem > configured) {
+    // the attribute is per device: one process may drive several GPUs (src/main.cpp -g 0,1,...)
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -3;
+    if (smem > configured[dev]) {
         if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-        configured = smem;
+        configured[dev] = smem;
     }
     int ntiles = a.tiles_x * a.tiles_y;
     int grid = ntiles < a.num_sms ? ntiles : a.num_sms;

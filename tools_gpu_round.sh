@@ -1,11 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-# (1) launch list of the fused path: 3 frames at 1080p; the last frame's launches are the steady state
-(timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_1080p_fused.csv python tools/profile_frame.py 1080p > gpurun_out/ncu_frame_stdout.txt 2>&1)
-wc -l gpurun_out/launches_1080p_fused.csv
-# (2) full capture of the dominant tensor-core kernel, alone
-(timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_1080p python tools/profile_tc.py 1080p > gpurun_out/ncu_tc_stdout.txt 2>&1)
-(timeout 300 ncu --set full --clock-control none -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_4k python tools/profile_tc.py 4k >> gpurun_out/ncu_tc_stdout.txt 2>&1)
-# (3) full capture of the HBM kernels of the last frame (head x4, update x3, tail, preproc x2 = 10 per frame; skip 2 frames + self-check)
-(timeout 400 ncu --set full --clock-control none -k regex:"head|update_kernel|tail_kernel|preproc" -s 20 -c 10 -o gpurun_out/prof_hbm_1080p python tools/profile_frame.py 1080p > gpurun_out/ncu_hbm_stdout.txt 2>&1)
-ls -la gpurun_out | head -30
+(timeout 900 python -m pytest tests -m gpu -q --durations=8 2>&1 | tail -25) > gpurun_out/all_gpu_tests.txt
+tail -14 gpurun_out/all_gpu_tests.txt
+for lanes in 3 4; do
+(timeout 300 python bench.py --steps 5 --warmup 3 --lanes $lanes --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_1080p_l$lanes.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_1080p_l$lanes.txt'));print('lanes',$lanes,d['value'],d['e2e']['value'])"
+done
+(timeout 300 python bench.py --steps 5 --warmup 3 --lanes 3 --workload 4k --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_4k_l3.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_4k_l3.txt'));print('4k lanes 3',d['value'],d['e2e']['value'])"
+(timeout 300 python bench.py --steps 3 --warmup 3 --model rife-v4 --timestep 0.25 --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_v4_1080p.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_v4_1080p.txt'));print('rife-v4 1080p t=0.25',d['value'],d['e2e']['value'])"
+RIFE_BENCH_PAIRS=2 timeout 600 python bench.py --steps 3 --warmup 3 --model rife-anime --tta --tta-temporal --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_anime_tta.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_anime_tta.txt'));print('anime -x -z 1080p',d['value'],d['e2e']['value'])"
+(timeout 300 python bench.py --steps 5 --warmup 3 2>&1 | tail -1) > gpurun_out/bench_1080p_default.txt
+cat gpurun_out/bench_1080p_default.txt
+(timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1) > gpurun_out/bench_reference.txt
+cat gpurun_out/bench_reference.txt
