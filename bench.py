@@ -163,7 +163,8 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=0, help="pairs per lock-step batch on the fused path (0 = auto from the frame size)")
     ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
     ap.add_argument("--tta", action="store_true")
     ap.add_argument("--tta-temporal", action="store_true")
@@ -212,6 +213,7 @@ def main():
         eng.load(md)
     eng.set_option("precision", args.precision)
     eng.set_option("lanes", args.lanes)
+    eng.set_option("batch", args.batch)
 
     # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
     nframes = min(PAIRS_PER_STEP, DISTINCT_FRAMES - 1) + 1
@@ -271,11 +273,14 @@ def main():
     for _ in range(2):
         eng.process_batch_ptr(in0, in1, w, h, ts, outp)
     barrier()
+    cb0 = pkg.copy_bytes()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng.process_batch_ptr(in0, in1, w, h, ts, outp)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    cb1 = pkg.copy_bytes()
+    h2d_step, d2h_step = (cb1[0] - cb0[0]) // args.steps, (cb1[1] - cb0[1]) // args.steps
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -319,11 +324,12 @@ def main():
                 "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
                 "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
-                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "fused_v46_path": bool(eng.get_option("fast_active")),
+                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch, "fused_v46_path": bool(eng.get_option("fast_active")),
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
                 "gflop_per_frame": GFLOP_PER_FRAME[args.workload] if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
                 "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0 if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
-                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": 2 * nb * PAIRS_PER_STEP, "d2h_bytes_per_step": nb * PAIRS_PER_STEP},
+                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                        "note": "bytes counted by the library; a frame shared by consecutive pairs of a batch is uploaded once"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "out_checksum": checksum}
         print(json.dumps(line))
     if dist is not None:

@@ -104,6 +104,10 @@ int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w
 /* kernels launched by this library since process start (bench.py reports it as gpu_launches) */
 unsigned long long rife_b200_launch_count(void);
 
+/* bytes this library copied host->device / device->host since process start (bench.py reports them per step) */
+unsigned long long rife_b200_h2d_bytes(void);
+unsigned long long rife_b200_d2h_bytes(void);
+
 /* last error message of the handle (thread-unsafe convenience for diagnostics); never NULL */
 const char* rife_b200_last_error(rife_b200_t* handle);
 

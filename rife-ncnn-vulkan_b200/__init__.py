@@ -44,6 +44,8 @@ def lib():
     L.rife_b200_bench_conv.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci]
     L.rife_b200_selftest_conv.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, cf, vp, vp]
     L.rife_b200_launch_count.restype = ctypes.c_ulonglong
+    L.rife_b200_h2d_bytes.restype = ctypes.c_ulonglong
+    L.rife_b200_d2h_bytes.restype = ctypes.c_ulonglong
     L.rife_b200_last_error.argtypes = [vp]
     L.rife_b200_last_error.restype = ctypes.c_char_p
     L.rife_b200_destroy.argtypes = [vp]
@@ -56,7 +58,7 @@ EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife
            "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_get_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv",
            "rife_b200_debug_conv_timeline",
-           "rife_b200_launch_count", "rife_b200_last_error", "rife_b200_destroy"]
+           "rife_b200_launch_count", "rife_b200_h2d_bytes", "rife_b200_d2h_bytes", "rife_b200_last_error", "rife_b200_destroy"]
 
 
 def family_flags(model_name):
@@ -172,6 +174,10 @@ def debug_conv_timeline(cin, cout, h, w, split=True, max_ctas=148, gpuid=0):
 
 def launch_count():
     return int(lib().rife_b200_launch_count())
+
+
+def copy_bytes():
+    return int(lib().rife_b200_h2d_bytes()), int(lib().rife_b200_d2h_bytes())
 
 
 def device_count():

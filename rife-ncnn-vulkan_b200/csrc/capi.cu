@@ -137,6 +137,8 @@ int rife_b200_load_packed(rife_b200_t* h, const void* src, size_t bytes) {
 }
 
 unsigned long long rife_b200_launch_count(void) { return rife::g_launch_count; }
+unsigned long long rife_b200_h2d_bytes(void) { return rife::g_h2d_bytes; }
+unsigned long long rife_b200_d2h_bytes(void) { return rife::g_d2h_bytes; }
 
 const char* rife_b200_last_error(rife_b200_t* h) { return h ? h->eng->last_error.c_str() : "null handle"; }
 

@@ -183,6 +183,7 @@ int Engine::set_option(const std::string& key, int value) {
         return 0;
     }
     if (key == "fast") { use_fast_ = value; return 0; }
+    if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
     if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
     last_error = "unknown option " + key;
@@ -194,6 +195,7 @@ int Engine::get_option(const std::string& key, int* value) {
     if (key == "precision") *value = precision_;
     else if (key == "lanes") *value = (int)lanes_.size();
     else if (key == "fast") *value = use_fast_;
+    else if (key == "batch") *value = batch_;
     else if (key == "fast_active") *value = fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1;
     else { last_error = "unknown option " + key; return -1; }
     return 0;
@@ -262,37 +264,53 @@ Tensor Engine::keep(const Tensor& t, DevBuf& b, cudaStream_t st) {
     return o;
 }
 
-int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out) {
-    if (!in0 || !in1 || !out || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
-    if (!loaded_) { last_error = "process before load"; return -4; }
-    size_t n = (size_t)w * h * 3;
-    if (t == 0.f) { if (out != in0) memcpy(out, in0, n); return 0; }  // rife.cpp:3206-3216
-    if (t == 1.f) { if (out != in1) memcpy(out, in1, n); return 0; }
-    std::lock_guard<std::mutex> lk(mu_);
-    cudaSetDevice(gpuid_);
-    Lane& L = *lanes_[0];
-    for (int i = 0; i < 3; i++)
-        if (u8_[i].ensure(n)) { last_error = "cudaMalloc failed"; return -2; }
-    cudaMemcpyAsync(u8_[0].p, in0, n, cudaMemcpyHostToDevice, L.st);
-    cudaMemcpyAsync(u8_[1].p, in1, n, cudaMemcpyHostToDevice, L.st);
-    int r = run_device(L, u8_[0].u8(), u8_[1].u8(), w, h, t, u8_[2].u8(), L.st);
-    if (r) return r;
-    cudaMemcpyAsync(out, u8_[2].p, n, cudaMemcpyDeviceToHost, L.st);
-    cudaError_t e = cudaStreamSynchronize(L.st);
-    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+// pairs per lock-step batch: enough images to fill the machine in the coarse IFBlocks (about one 4K frame of pixels)
+int Engine::batch_for(int w, int h) const {
+    if (!(fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1)) return 1;
+    if (batch_ > 0) return batch_;
+    const size_t px = (size_t)((w + 31) / 32 * 32) * ((h + 31) / 32 * 32);
+    size_t b = (size_t)2 * 3840 * 2176 / (px ? px : 1);  // measured: 8 pairs at 1080p, 2 at 4K (profiles/README.md)
+    if (b < 1) b = 1;
+    if (b > V46_MAX_BATCH) b = V46_MAX_BATCH;
+    return (int)b;
+}
+
+// n pairs on one lane: one lock-step batch on the fused path, otherwise pair by pair
+int Engine::run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st) {
+    if (n > 1 && fast_ok_ && use_fast_ && L.fast && v4_ && !tta_ && !ttat_ && precision_ == 1) {
+        std::string err;
+        int r = L.fast->run_batch(n, d_in0, d_in1, w, h, ts, d_out, st, err);
+        if (r) { last_error = err; return -5; }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
+        return 0;
+    }
+    for (int i = 0; i < n; i++) {
+        int r = run_device(L, d_in0[i], d_in1[i], w, h, ts[i], d_out[i], st);
+        if (r) return r;
+    }
     return 0;
+}
+
+int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out) {
+    const uint8_t* a[1] = {in0};
+    const uint8_t* b[1] = {in1};
+    uint8_t* o[1] = {out};
+    if (!in0 || !in1 || !out) { last_error = "bad argument"; return -1; }
+    return process_batch(1, a, b, w, h, &t, o);
 }
 
 int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out) {
     const uint8_t* a[1] = {d_in0};
     const uint8_t* b[1] = {d_in1};
     uint8_t* o[1] = {d_out};
+    if (!d_in0 || !d_in1 || !d_out) { last_error = "bad argument"; return -1; }
     return process_batch_device(1, a, b, w, h, &t, o);
 }
 
-// Frames already in device memory.  Pairs are dealt round-robin to the lanes; when the caller supplied a stream
-// (set_stream) every lane first waits for that stream and the stream finally waits for every lane, so events the
-// caller records on it bracket all of the work.
+// Frames already in device memory.  Pairs are cut into chunks (lock-step batches on the fused path) that are dealt
+// round-robin to the lanes; when the caller supplied a stream (set_stream) every lane first waits for that stream and
+// the stream finally waits for every lane, so events the caller records on it bracket all of the work.
 int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out) {
     if (n < 0 || !d_in0 || !d_in1 || !d_out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
     if (!loaded_) { last_error = "process before load"; return -4; }
@@ -300,35 +318,53 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
     const int nl = (int)lanes_.size();
+    const int B = batch_for(w, h);
     if (use_user_stream_) {
         cudaEventRecord(ev_entry_, user_stream_);
-        for (int l = 0; l < nl && l < n; l++) cudaStreamWaitEvent(lanes_[l]->st, ev_entry_, 0);
+        for (int l = 0; l < nl; l++) cudaStreamWaitEvent(lanes_[l]->st, ev_entry_, 0);
     }
-    for (int i = 0; i < n; i++) {
-        if (!d_in0[i] || !d_in1[i] || !d_out[i]) { last_error = "null frame pointer"; return -1; }
-        Lane& L = *lanes_[i % nl];
-        if (ts[i] == 0.f || ts[i] == 1.f) {
-            cudaMemcpyAsync(d_out[i], ts[i] == 0.f ? d_in0[i] : d_in1[i], nb, cudaMemcpyDeviceToDevice, L.st);
-        } else {
-            int r = run_device(L, d_in0[i], d_in1[i], w, h, ts[i], d_out[i], L.st);
+    const uint8_t* c0[V46_MAX_BATCH];
+    const uint8_t* c1[V46_MAX_BATCH];
+    uint8_t* co[V46_MAX_BATCH];
+    float ct[V46_MAX_BATCH];
+    int cn = 0, chunk = 0;
+    // spread the work: no more pairs per chunk than needed to give every lane something to do
+    int per = B;
+    if (n < per * nl) per = (n + nl - 1) / nl;
+    if (per < 1) per = 1;
+    for (int i = 0; i <= n; i++) {
+        if (i < n) {
+            if (!d_in0[i] || !d_in1[i] || !d_out[i]) { last_error = "null frame pointer"; return -1; }
+            if (ts[i] == 0.f || ts[i] == 1.f) {  // rife.cpp:3206-3216: the output is an input
+                cudaMemcpyAsync(d_out[i], ts[i] == 0.f ? d_in0[i] : d_in1[i], nb, cudaMemcpyDeviceToDevice, lanes_[chunk % nl]->st);
+                continue;
+            }
+            c0[cn] = d_in0[i]; c1[cn] = d_in1[i]; co[cn] = d_out[i]; ct[cn] = ts[i];
+            cn++;
+        }
+        if (cn == per || (i == n && cn > 0)) {
+            Lane& L = *lanes_[chunk % nl];
+            int r = run_chunk(L, cn, c0, c1, w, h, ct, co, L.st);
             if (r) return r;
+            cn = 0;
+            chunk++;
         }
     }
-    for (int l = 0; l < nl && l < n; l++) {
+    for (int l = 0; l < nl; l++) {
         cudaEventRecord(lanes_[l]->done, lanes_[l]->st);
         if (use_user_stream_) cudaStreamWaitEvent(user_stream_, lanes_[l]->done, 0);
     }
     if (async_) return 0;
     cudaError_t e = cudaSuccess;
-    for (int l = 0; l < nl && l < n; l++) { cudaError_t e2 = cudaStreamSynchronize(lanes_[l]->st); if (e2 != cudaSuccess) e = e2; }
+    for (int l = 0; l < nl; l++) { cudaError_t e2 = cudaStreamSynchronize(lanes_[l]->st); if (e2 != cudaSuccess) e = e2; }
     if (use_user_stream_) { cudaError_t e2 = cudaStreamSynchronize(user_stream_); if (e2 != cudaSuccess) e = e2; }
     if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
-// Host frames, pipelined: slot s = i mod (2 * lanes) owns three device frame buffers; H2D runs on one copy stream,
-// compute on lane i mod lanes, D2H on the other copy stream, chained with events (pinned host memory makes the copies
-// truly asynchronous; pageable memory still works, the driver then stages synchronously).
+// Host frames, pipelined by chunk: slot s = chunk mod (2 * lanes) owns 3 device frame buffers per batch position; H2D
+// runs on one copy stream, compute on lane chunk mod lanes, D2H on the other copy stream, chained with events (pinned
+// host memory makes the copies truly asynchronous; pageable memory still works, the driver then stages synchronously).
 int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out) {
     if (n < 0 || !in0 || !in1 || !out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
     if (!loaded_) { last_error = "process before load"; return -4; }
@@ -337,33 +373,77 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     cudaSetDevice(gpuid_);
     const int nl = (int)lanes_.size();
     const int nslots = 2 * nl <= kSlots ? 2 * nl : kSlots;
-    for (int i = 0; i < 3 * nslots; i++)
-        if (u8_[i].ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
+    const int B = batch_for(w, h);
+    int per = B;
+    if (n < per * nl) per = (n + nl - 1) / nl;
+    if (per < 1) per = 1;
+    if (u8_.size() < (size_t)kSlots * 3 * V46_MAX_BATCH) u8_.resize((size_t)kSlots * 3 * V46_MAX_BATCH);
+    auto buf = [&](int slot, int pos, int which) -> DevBuf& { return u8_[((size_t)slot * V46_MAX_BATCH + pos) * 3 + which]; };
     std::vector<int> used(nslots, 0);
-    for (int i = 0; i < n; i++) {
-        if (!in0[i] || !in1[i] || !out[i]) { last_error = "null frame pointer"; return -1; }
-        if (ts[i] == 0.f || ts[i] == 1.f) {
-            memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);  // host-side copy, touches nothing queued
-            continue;
+    const uint8_t* c0[V46_MAX_BATCH];
+    const uint8_t* c1[V46_MAX_BATCH];
+    uint8_t* co[V46_MAX_BATCH];
+    uint8_t* ho[V46_MAX_BATCH];
+    float ct[V46_MAX_BATCH];
+    const uint8_t* up_host[2 * V46_MAX_BATCH];
+    const uint8_t* up_dev[2 * V46_MAX_BATCH];
+    int nup = 0;
+    int cn = 0, chunk = 0;
+    for (int i = 0; i <= n; i++) {
+        if (i < n) {
+            if (!in0[i] || !in1[i] || !out[i]) { last_error = "null frame pointer"; return -1; }
+            if (ts[i] == 0.f || ts[i] == 1.f) {
+                if (out[i] != (ts[i] == 0.f ? in0[i] : in1[i])) memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);  // host-side copy, touches nothing queued
+                continue;
+            }
+            const int s = chunk % nslots;
+            if (cn == 0) {
+                if (used[s]) cudaStreamWaitEvent(st_copy_[0], ev_comp_[s], 0);  // inputs of slot s are free once its compute finished
+                nup = 0;
+            }
+            // a frame shared by consecutive pairs of the chunk (pair k's in1 is pair k+1's in0 in a stream) is uploaded once:
+            // the slot holds up to 2*B distinct input frames, found again by host pointer
+            const uint8_t* hp2[2] = {in0[i], in1[i]};
+            const uint8_t* dp2[2];
+            for (int k = 0; k < 2; k++) {
+                int found = -1;
+                for (int u = 0; u < nup; u++)
+                    if (up_host[u] == hp2[k]) { found = u; break; }
+                if (found < 0) {
+                    DevBuf& bi = buf(s, nup >> 1, nup & 1);
+                    if (bi.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
+                    cudaMemcpyAsync(bi.p, hp2[k], nb, cudaMemcpyHostToDevice, st_copy_[0]);
+                    g_h2d_bytes += nb;
+                    up_host[nup] = hp2[k];
+                    up_dev[nup] = bi.u8();
+                    found = nup++;
+                }
+                dp2[k] = up_dev[found];
+            }
+            DevBuf& b2 = buf(s, cn, 2);
+            if (b2.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
+            const uint8_t* b0p = dp2[0];
+            const uint8_t* b1p = dp2[1];
+            c0[cn] = b0p; c1[cn] = b1p; co[cn] = b2.u8(); ho[cn] = out[i]; ct[cn] = ts[i];
+            cn++;
         }
-        const int s = i % nslots;
-        Lane& L = *lanes_[i % nl];
-        uint8_t* d0 = u8_[s * 3 + 0].u8();
-        uint8_t* d1 = u8_[s * 3 + 1].u8();
-        uint8_t* dout = u8_[s * 3 + 2].u8();
-        if (used[s]) cudaStreamWaitEvent(st_copy_[0], ev_comp_[s], 0);  // inputs of slot s are free once its compute finished
-        cudaMemcpyAsync(d0, in0[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
-        cudaMemcpyAsync(d1, in1[i], nb, cudaMemcpyHostToDevice, st_copy_[0]);
-        cudaEventRecord(ev_h2d_[s], st_copy_[0]);
-        cudaStreamWaitEvent(L.st, ev_h2d_[s], 0);
-        if (used[s]) cudaStreamWaitEvent(L.st, ev_d2h_[s], 0);  // output buffer of slot s has been downloaded
-        int r = run_device(L, d0, d1, w, h, ts[i], dout, L.st);
-        if (r) return r;
-        cudaEventRecord(ev_comp_[s], L.st);
-        cudaStreamWaitEvent(st_copy_[1], ev_comp_[s], 0);
-        cudaMemcpyAsync(out[i], dout, nb, cudaMemcpyDeviceToHost, st_copy_[1]);
-        cudaEventRecord(ev_d2h_[s], st_copy_[1]);
-        used[s] = 1;
+        if (cn == per || (i == n && cn > 0)) {
+            const int s = chunk % nslots;
+            Lane& L = *lanes_[chunk % nl];
+            cudaEventRecord(ev_h2d_[s], st_copy_[0]);
+            cudaStreamWaitEvent(L.st, ev_h2d_[s], 0);
+            if (used[s]) cudaStreamWaitEvent(L.st, ev_d2h_[s], 0);  // output buffers of slot s have been downloaded
+            int r = run_chunk(L, cn, c0, c1, w, h, ct, co, L.st);
+            if (r) return r;
+            cudaEventRecord(ev_comp_[s], L.st);
+            cudaStreamWaitEvent(st_copy_[1], ev_comp_[s], 0);
+            for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, st_copy_[1]);
+            g_d2h_bytes += (unsigned long long)cn * nb;
+            cudaEventRecord(ev_d2h_[s], st_copy_[1]);
+            used[s] = 1;
+            cn = 0;
+            chunk++;
+        }
     }
     cudaError_t e = cudaStreamSynchronize(st_copy_[0]);
     for (Lane* L : lanes_) { cudaError_t e2 = cudaStreamSynchronize(L->st); if (e2 != cudaSuccess) e = e2; }

@@ -81,7 +81,10 @@ private:
     cudaEvent_t ev_h2d_[kSlots] = {}, ev_comp_[kSlots] = {}, ev_d2h_[kSlots] = {}, ev_entry_ = nullptr;
     std::mutex mu_;
     // device buffers
-    DevBuf u8_[3 * kSlots];  // staged in0,in1,out per pipeline slot
+    std::vector<DevBuf> u8_;  // staged in0,in1,out per pipeline slot and batch position
+    int batch_ = 0;           // pairs per lock-step batch on the fused path (0 = choose from the frame size)
+    int batch_for(int w, int h) const;
+    int run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st);
 };
 
 }  // namespace rife

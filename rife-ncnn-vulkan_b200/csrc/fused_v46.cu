@@ -88,9 +88,21 @@ __device__ __forceinline__ void store_c8_s2d_16(__half* out, const float* v, int
 }
 
 // x0 = Interp(cat(I0, I1, T), 1/8): flownet.param:9-10
-__global__ void head0_kernel(const float* __restrict__ I0, const float* __restrict__ I1, float t, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+struct TBatch {
+    float t[V46_MAX_BATCH];
+};
+struct OutBatch {
+    uint8_t* p[V46_MAX_BATCH];
+};
+
+__global__ void head0_kernel(const float* __restrict__ I0, const float* __restrict__ I1, TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
+    const int b = blockIdx.z;
+    const float t = tb.t[b];
+    I0 += (size_t)b * 3 * hp * wp;
+    I1 += (size_t)b * 3 * hp * wp;
+    out += (size_t)b * 16 * oh * ow * 2;
     int sx, sy;
     float fx, fy;
     lin_coeff(ox, wp, ow, sx, fx);
@@ -111,11 +123,18 @@ __global__ void head0_kernel(const float* __restrict__ I0, const float* __restri
 
 // block head for k >= 1: flownet.param:50-62 (S = 4), :106-115 (2), :158-165 (1)
 template <int S>
-__global__ void head_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M, float t,
+__global__ void head_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M, TBatch tb,
                             int hp, int wp, int oh, int ow, __half* __restrict__ out) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
     const size_t plane = (size_t)hp * wp;
+    const int b = blockIdx.z;
+    const float t = tb.t[b];
+    I0 += (size_t)b * 3 * plane;
+    I1 += (size_t)b * 3 * plane;
+    F += (size_t)b * 4 * plane;
+    M += (size_t)b * plane;
+    out += (size_t)b * 16 * oh * ow * 2;
     float v[16];
     // 8-channel vector cat(W0, W1, T, M) and the 4 flow channels at one full-resolution pixel
     auto at = [&](int y, int x, float* e) {
@@ -168,6 +187,9 @@ template <int S, bool FIRST>
 __global__ void update_kernel(const float* __restrict__ d, int dh, int dw, float* __restrict__ F, float* __restrict__ M, int hp, int wp) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= wp) return;
+    d += (size_t)blockIdx.z * 6 * dh * dw;
+    F += (size_t)blockIdx.z * 4 * hp * wp;
+    M += (size_t)blockIdx.z * hp * wp;
     int sx, sy;
     float fx, fy;
     lin_coeff(x, dw, wp, sx, fx);
@@ -187,9 +209,15 @@ __global__ void update_kernel(const float* __restrict__ d, int dh, int dw, float
 
 // last update + blend + rife_postproc: flownet.param:202-217, src/rife.cpp:4375-4398, mat_pixel.cpp:158
 __global__ void tail_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M,
-                            const float* __restrict__ d3, int hp, int wp, uint8_t* __restrict__ rgb, int w, int h) {
+                            const float* __restrict__ d3, int hp, int wp, OutBatch ob, int w, int h) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
+    {
+        const size_t pl = (size_t)hp * wp;
+        const int b = blockIdx.z;
+        I0 += (size_t)b * 3 * pl; I1 += (size_t)b * 3 * pl; F += (size_t)b * 4 * pl; M += (size_t)b * pl; d3 += (size_t)b * 6 * pl;
+    }
+    uint8_t* __restrict__ rgb = ob.p[blockIdx.z];
     // the reference CPU path reads the first w*h floats of each padded output channel contiguously (rife.cpp:4375-4387)
     const size_t idx = (size_t)y * w + x;
     const int Y = (int)(idx / wp), X = (int)(idx - (size_t)Y * wp);
@@ -254,9 +282,10 @@ V46Runner::~V46Runner() {
     for (void* p : bufs_) cudaFree(p);
 }
 
-int V46Runner::ensure(int w, int h, std::string& err) {
+int V46Runner::ensure(int w, int h, int batch, std::string& err) {
     const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
-    if (wp == wp_ && hp == hp_) return 0;
+    if (wp == wp_ && hp == hp_ && batch <= cap_) return 0;
+    const size_t B = (size_t)batch;
     for (void* p : bufs_) cudaFree(p);
     bufs_.clear();
     auto alloc = [&](size_t bytes) -> void* {
@@ -266,10 +295,10 @@ int V46Runner::ensure(int w, int h, std::string& err) {
         return p;
     };
     const size_t plane = (size_t)wp * hp;
-    I0_ = (float*)alloc(3 * plane * 4);
-    I1_ = (float*)alloc(3 * plane * 4);
-    F_ = (float*)alloc(4 * plane * 4);
-    M_ = (float*)alloc(plane * 4);
+    I0_ = (float*)alloc(B * 3 * plane * 4);
+    I1_ = (float*)alloc(B * 3 * plane * 4);
+    F_ = (float*)alloc(B * 4 * plane * 4);
+    M_ = (float*)alloc(B * plane * 4);
     static const int S[4] = {8, 4, 2, 1};
     bool fail = !I0_ || !I1_ || !F_ || !M_;
     for (int k = 0; k < 4; k++) {
@@ -277,20 +306,21 @@ int V46Runner::ensure(int w, int h, std::string& err) {
         const int c = 192 >> 0;
         (void)c;
         static const int cw[4] = {192, 128, 96, 64};
-        d_[k] = (float*)alloc(6 * hk * wk * 4);
-        x_[k] = (__half*)alloc((size_t)16 * hk * wk * 2 * 2);                         // head, C8 s2d, hi+lo
-        y0_[k] = (__half*)alloc((size_t)(cw[k] / 2) * (hk / 2) * (wk / 2) * 2 * 2);   // conv0 out, C8 s2d
-        a_[k] = (__half*)alloc((size_t)cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain ping
-        b_[k] = (__half*)alloc((size_t)cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain pong
+        d_[k] = (float*)alloc(B * 6 * hk * wk * 4);
+        x_[k] = (__half*)alloc(B * 16 * hk * wk * 2 * 2);                         // head, C8 s2d, hi+lo
+        y0_[k] = (__half*)alloc(B * (cw[k] / 2) * (hk / 2) * (wk / 2) * 2 * 2);   // conv0 out, C8 s2d
+        a_[k] = (__half*)alloc(B * cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain ping
+        b_[k] = (__half*)alloc(B * cw[k] * (hk / 4) * (wk / 4) * 2 * 2);          // residual chain pong
         fail = fail || !d_[k] || !x_[k] || !y0_[k] || !a_[k] || !b_[k];
     }
-    if (fail) { err = "cudaMalloc failed"; wp_ = hp_ = 0; return -2; }
+    if (fail) { err = "cudaMalloc failed"; wp_ = hp_ = 0; cap_ = 0; return -2; }
     wp_ = wp;
     hp_ = hp;
+    cap_ = batch;
     return 0;
 }
 
-int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, cudaStream_t st) {
+int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, int batch, cudaStream_t st) {
     const Layer& L = net_->layers[li];
     const DeviceWeights& W = wr_->weights(li);
     TcConvArgs a;
@@ -301,7 +331,10 @@ int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, fl
     a.split_in = 1;
     a.s2 = W.tc_s2;
     a.num_sms = wr_->num_sms;
+    a.batch = batch;
+    a.in_bstride = (size_t)(W.tc_s2 ? 4 : 1) * W.cinp * oh * ow * 2;  // hi + lo planes of one image
     if (L.type == "Convolution") {
+        a.out_bstride = a.res_bstride = (size_t)L.geti(0, 0) * oh * ow * 2;
         a.epi = TC_EPI_C8;
         a.out = out;
         a.out_plane = (size_t)a.Cout * oh * ow;
@@ -316,43 +349,58 @@ int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, fl
         a.out_f32 = out_f32;
         a.ocs = W.ocs;
         a.ps = 2;
+        a.outf_bstride = (size_t)6 * (oh * 4) * (ow * 4);
     }
     return launch_tc_conv(a, in, st);
 }
 
 int V46Runner::run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err) {
+    return run_batch(1, &d_in0, &d_in1, w, h, &t, &d_out, st, err);
+}
+
+// n <= V46_MAX_BATCH pairs in lock-step: every kernel covers all n images (blockIdx.z / the image-major tile index of the
+// conv), so the latency-bound small blocks (17-136 CTAs per image at 1080p) fill the machine.
+int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out,
+                         cudaStream_t st, std::string& err) {
     if (!ok_) { err = "fast path not initialised"; return -1; }
-    if (ensure(w, h, err)) return -2;
+    if (n < 1 || n > V46_MAX_BATCH) { err = "bad batch size"; return -1; }
+    if (ensure(w, h, n, err)) return -2;
     const int wp = wp_, hp = hp_;
+    const size_t plane = (size_t)wp * hp;
     static const int S[4] = {8, 4, 2, 1};
-    launch_preproc(d_in0, w, h, I0_, wp, hp, 0, st);
-    launch_preproc(d_in1, w, h, I1_, wp, hp, 0, st);
+    TBatch tb;
+    OutBatch ob;
+    for (int b = 0; b < V46_MAX_BATCH; b++) { tb.t[b] = b < n ? ts[b] : 0.f; ob.p[b] = b < n ? d_out[b] : nullptr; }
+    for (int b = 0; b < n; b++) {
+        launch_preproc(d_in0[b], w, h, I0_ + (size_t)b * 3 * plane, wp, hp, 0, st);
+        launch_preproc(d_in1[b], w, h, I1_ + (size_t)b * 3 * plane, wp, hp, 0, st);
+    }
     for (int k = 0; k < 4; k++) {
         const int hk = hp / S[k], wk = wp / S[k];
-        dim3 g(cdiv(wk, 128), hk);
-        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(I0_, I1_, t, hp, wp, hk, wk, x_[0]);
-        else if (k == 1) head_kernel<4><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[1]);
-        else if (k == 2) head_kernel<2><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[2]);
-        else head_kernel<1><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, t, hp, wp, hk, wk, x_[3]);
+        dim3 g(cdiv(wk, 128), hk, n);
+        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(I0_, I1_, tb, hp, wp, hk, wk, x_[0]);
+        else if (k == 1) head_kernel<4><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[1]);
+        else if (k == 2) head_kernel<2><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[2]);
+        else head_kernel<1><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
         const int* L = &conv_[k * 11];
-        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, st);   // 3x3 s2, leaky
-        r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, st);     // 3x3 s2, leaky
+        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, st);   // 3x3 s2, leaky
+        r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, n, st);     // 3x3 s2, leaky
         __half* cur = a_[k];
         __half* nxt = b_[k];
-        for (int j = 0; j < 8; j++) {                                                  // y = leaky(conv(y) + y)
-            r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, st);
+        for (int j = 0; j < 8; j++) {                                                     // y = leaky(conv(y) + y)
+            r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, n, st);
             __half* tmp = cur; cur = nxt; nxt = tmp;
         }
-        r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, st);       // deconv + PixelShuffle -> flow<k>
+        r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, n, st);       // deconv + PixelShuffle -> flow<k>
         if (r) { err = "tensor-core conv launch failed in block " + std::to_string(k); return -3; }
-        dim3 gf(cdiv(wp, 128), hp);
+        dim3 gf(cdiv(wp, 128), hp, n);
         if (k == 0) update_kernel<8, true><<<gf, 128, 0, st>>>(d_[0], hk, wk, F_, M_, hp, wp);
         else if (k == 1) update_kernel<4, false><<<gf, 128, 0, st>>>(d_[1], hk, wk, F_, M_, hp, wp);
         else if (k == 2) update_kernel<2, false><<<gf, 128, 0, st>>>(d_[2], hk, wk, F_, M_, hp, wp);
         if (k < 3) g_launch_count++;
     }
-    tail_kernel<<<dim3(cdiv(w, 128), h), 128, 0, st>>>(I0_, I1_, F_, M_, d_[3], hp, wp, d_out, w, h);
+    tail_kernel<<<dim3(cdiv(w, 128), h, n), 128, 0, st>>>(I0_, I1_, F_, M_, d_[3], hp, wp, ob, w, h);
     g_launch_count++;
     return 0;
 }

@@ -12,6 +12,8 @@
 
 namespace rife {
 
+constexpr int V46_MAX_BATCH = 8;
+
 class V46Runner {
 public:
     ~V46Runner();
@@ -19,16 +21,18 @@ public:
     int init(const Net* net, const NetRunner* weights, std::string& err);
     bool ok() const { return ok_; }
     int run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err);
+    int run_batch(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st,
+                  std::string& err);
 
 private:
-    int ensure(int w, int h, std::string& err);
-    int conv(int layer, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, cudaStream_t st);
+    int ensure(int w, int h, int batch, std::string& err);
+    int conv(int layer, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, int batch, cudaStream_t st);
     const Net* net_ = nullptr;
     const NetRunner* wr_ = nullptr;
     bool ok_ = false;
     float slope_ = 0.2f;
     std::vector<int> conv_;  // the 44 conv / deconv layer indices in graph order
-    int wp_ = 0, hp_ = 0;
+    int wp_ = 0, hp_ = 0, cap_ = 0;
     std::vector<void*> bufs_;
     float *I0_ = nullptr, *I1_ = nullptr, *F_ = nullptr, *M_ = nullptr, *d_[4] = {};
     __half *x_[4] = {}, *y0_[4] = {}, *a_[4] = {}, *b_[4] = {};

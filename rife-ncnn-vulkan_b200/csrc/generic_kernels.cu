@@ -9,6 +9,7 @@
 namespace rife {
 
 unsigned long long g_launch_count = 0;
+unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
 
 static inline unsigned int cdiv(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
 

@@ -8,6 +8,7 @@ namespace rife {
 
 // counts kernel launches issued by this library (reported by bench.py as gpu_launches)
 extern unsigned long long g_launch_count;
+extern unsigned long long g_h2d_bytes, g_d2h_bytes;
 
 struct ConvArgs {
     const float* in;

@@ -60,9 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spins > (1u << 26)) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     float* slope_s = bias_s + N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = a.tiles_x * a.tiles_y;
+    const int tiles_img = a.tiles_x * a.tiles_y;
+    const int ntiles = tiles_img * a.batch;  // image-major: tile -> (image, ty, tx)
     const int KCP = a.Cin / 16;                    // K chunks per parity sub-image (all of them for stride 1)
     const int KC = TAPS == 9 ? KCP : 4 * KCP;
 
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+                const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
+                const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
                 const int x0 = tx * TVALID, y0 = ty * (2 * MT);
                 for (int kc = 0; kc < KC; kc++, it++) {
                     const int s = it % STAGES;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + W_BYTES));
                     for (int p = 0; p < nplanes; p++)
-                        tma_load_3d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc);
+                        tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc, bimg);
                     bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                     if (dbg && it < 12) dbg[1 + it] = clock64();
                 }
@@ -288,9 +290,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int buf = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
-            const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+            const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
+            const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
             const int x0 = tx * TVALID, y0 = ty * (2 * MT);
             const int x = x0 + xr;
+            const __half* res_b = a.res + (size_t)bimg * a.res_bstride;
+            __half* out_b = a.out + (size_t)bimg * a.out_bstride;
+            float* outf_b = a.out_f32 + (size_t)bimg * a.outf_bstride;
             const bool xvalid = xr < TVALID && x < a.W;
             if (a.epi == TC_EPI_C8) {
                 // v = act(acc + bias + m1*res) + m2*res with per-channel slopes from shared memory: one branch-free body
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const size_t off = ((size_t)(cb * G + g) * HW + (size_t)y * a.W + x) * 8;
-                        dst[g] = __ldg(reinterpret_cast<const uint4*>(a.res + off));
-                        if (a.res_split) dst[G + g] = __ldg(reinterpret_cast<const uint4*>(a.res + a.res_plane + off));
+                        dst[g] = __ldg(reinterpret_cast<const uint4*>(res_b + off));
+                        if (a.res_split) dst[G + g] = __ldg(reinterpret_cast<const uint4*>(res_b + a.res_plane + off));
                     }
                 };
                 auto process = [&](int blk, const uint4* rcur) {
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
 #pragma unroll
                                 for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
                                 const size_t ooff = ((cg_base + cg) * cg_stride + pix) * 8;
-                                *reinterpret_cast<uint4*>(a.out + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                                *reinterpret_cast<uint4*>(out_b + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
                                                                                      *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
                                 if (a.split_out) {
                                     __half2 l[4];
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                         float2 f = __half22float2(h[k]);
                                         l[k] = __floats2half2_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
                                     }
-                                    *reinterpret_cast<uint4*>(a.out + a.out_plane + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                                    *reinterpret_cast<uint4*>(out_b + a.out_plane + ooff) = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
                                                                                                        *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
                                 }
                             }
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                     const int o0 = oc4 * 4 + sh * 2;  // oc for sw = 0
                                     float4 w4 = make_float4(v[o0], v[o0 + 1], v[OCS + o0], v[OCS + o0 + 1]);  // px = 0 | px = 1
                                     const int oy = (2 * y + py) * 2 + sh;
-                                    *reinterpret_cast<float4*>(a.out_f32 + ((size_t)oc4 * OH + oy) * OW + 4 * x) = w4;
+                                    *reinterpret_cast<float4*>(outf_b + ((size_t)oc4 * OH + oy) * OW + 4 * x) = w4;
                                 }
                             }
                         } else {
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             for (int oc = 0; oc < OCS; oc++) {
                                 if (oc >= a.Cout) break;
                                 float2 w2 = make_float2(v[oc], v[OCS + oc]);
-                                *reinterpret_cast<float2*>(a.out_f32 + ((size_t)oc * OH + 2 * y + py) * OW + 2 * x) = w2;
+                                *reinterpret_cast<float2*>(outf_b + ((size_t)oc * OH + 2 * y + py) * OW + 2 * x) = w2;
                             }
                         }
                     }
@@ -495,7 +501,7 @@ static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st)
         if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
         configured[dev] = smem;
     }
-    int ntiles = a.tiles_x * a.tiles_y;
+    int ntiles = a.tiles_x * a.tiles_y * a.batch;
     int grid = ntiles < a.num_sms ? ntiles : a.num_sms;
     tc_conv3x3_kernel<N, MT, STAGES, TAPS><<<grid, NTHREADS, smem, st>>>(tm, a);
     g_launch_count++;
@@ -523,11 +529,14 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     // stride 2: the input is the space-to-depth tensor, 4 sub-images of (H, W) = output size, Cin channels each
     const int cgroups = (a.s2 ? 4 : 1) * (a.Cin / 8);
     if (a.out_s2d && ((a.H | a.W) & 1)) return -7;
-    cuuint64_t dims[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups};
-    cuuint64_t strides[2] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16};
-    cuuint32_t box[3] = {(cuuint32_t)TWP * 4, (cuuint32_t)(2 * MT + 2), 2};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (a.batch < 1) a.batch = 1;
+    const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
+    if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
+    cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16, a.batch > 1 ? (cuuint64_t)a.in_bstride * 2 : (cuuint64_t)img_bytes};
+    cuuint32_t box[4] = {(cuuint32_t)TWP * 4, (cuuint32_t)(2 * MT + 2), 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -5;
     switch (a.N) {

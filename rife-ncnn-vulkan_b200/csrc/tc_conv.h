@@ -26,6 +26,8 @@ struct TcConvArgs {
     int res_mode;           // 0 none, 1 add before activation, 2 add after activation
     int act_mode;           // 0 none, 1 leaky(slope), 2 prelu, 3 sigmoid (deconv epilogue only)
     int ocs, ps;            // deconv: output-channel slots per parity, PixelShuffle factor (1 = none)
+    int batch;              // images per launch (0 / 1 = single); image b lives at base + b * *_bstride
+    size_t in_bstride, res_bstride, out_bstride, outf_bstride;  // elements of the respective tensors
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
