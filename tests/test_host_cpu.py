@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(pkg):
     hdr = open(os.path.join(ROOT, "include", "rife_b200.h")).read()
-    declared = set(re.findall(r"\b(rife_b200_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(rife_b200_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(pkg.EXPORTS), declared ^ set(pkg.EXPORTS)
     L = pkg.lib()
     for name in declared:
