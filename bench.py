@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--plain-blocks", type=int, default=-1, help="bit mask of IFBlocks whose residual chain uses plain fp16 activations (-1 = library default)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per lock-step batch on the fused path (0 = auto from the frame size)")
     ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
     ap.add_argument("--tta", action="store_true")
@@ -214,6 +215,8 @@ def main():
     eng.set_option("precision", args.precision)
     eng.set_option("lanes", args.lanes)
     eng.set_option("batch", args.batch)
+    if args.plain_blocks >= 0:
+        eng.set_option("plain_blocks", args.plain_blocks)
 
     # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
     nframes = min(PAIRS_PER_STEP, DISTINCT_FRAMES - 1) + 1
@@ -292,7 +295,8 @@ def main():
     burst, sustained, hbm, how = measured_peaks()
     hp, wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
     ch, cw = hp // 4, wp // 4
-    split = 1 if args.precision == 1 else 0
+    pmask = eng.get_option("plain_blocks") if eng.get_option("fast_active") else 0
+    split = 1 if (args.precision == 1 and not (pmask & 8)) else 0  # block 3's residual chain: plain fp16 when bit 3 is set
     iters = 20
     with torch.cuda.stream(stream):
         pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, 3, gpuid=local)
@@ -306,7 +310,7 @@ def main():
     flop = 2.0 * 9 * 64 * 64 * ch * cw  # algorithmic FLOPs of the layer; the hi+lo split issues 2x this on the tensor pipe
     achieved = flop / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md)
-    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else None
+    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else {(272, 480): 17.6e6}.get((ch, cw))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
                 "kernel": "tc_conv3x3_kernel<64,4,3> %dx%d" % (cw, ch), "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
                 "tensor_issue_multiplier": 2 if split else 1}
@@ -321,10 +325,11 @@ def main():
         nb = w * h * 3
         line = {"metric": "interpolated frames/sec (%s)" % args.model, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands (split hi+lo) / f32 accumulate" if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
+                "dtype": ("f16 operands / f32 accumulate (split hi+lo operands in block heads%s)" % ("" if pmask == 15 else " and IFBlocks " + ",".join(str(k) for k in range(4) if not (pmask >> k) & 1)))
+                         if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
                 "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
-                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch, "fused_v46_path": bool(eng.get_option("fast_active")),
+                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch, "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "fused_v46_path": bool(eng.get_option("fast_active")),
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
                 "gflop_per_frame": GFLOP_PER_FRAME[args.workload] if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
                 "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0 if args.model == MODEL and not (args.tta or args.tta_temporal) else None,

@@ -183,6 +183,11 @@ int Engine::set_option(const std::string& key, int value) {
         return 0;
     }
     if (key == "fast") { use_fast_ = value; return 0; }
+    if (key == "plain_blocks") {  // bit mask of IFBlocks whose residual chain uses plain fp16 activations (fused path)
+        plain_mask_ = value & 15;
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_plain_mask(plain_mask_);
+        return 0;
+    }
     if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
     if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
@@ -196,6 +201,7 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "lanes") *value = (int)lanes_.size();
     else if (key == "fast") *value = use_fast_;
     else if (key == "batch") *value = batch_;
+    else if (key == "plain_blocks") *value = plain_mask_;
     else if (key == "fast_active") *value = fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1;
     else { last_error = "unknown option " + key; return -1; }
     return 0;
@@ -254,6 +260,7 @@ void Engine::setup_fast() {
     d0.release(); d1.release(); dout.release();
     fast_ok_ = ok;
     if (!ok) for (Lane* LL : lanes_) { delete LL->fast; LL->fast = nullptr; }
+    else for (Lane* LL : lanes_) LL->fast->set_plain_mask(plain_mask_);
 }
 
 Tensor Engine::keep(const Tensor& t, DevBuf& b, cudaStream_t st) {

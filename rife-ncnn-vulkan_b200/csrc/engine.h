@@ -70,6 +70,7 @@ private:
     bool async_ = false;
     bool fast_ok_ = false;  // the fused v4.6 path reproduced the generic executor on the self-check
     int use_fast_ = 1;
+    int plain_mask_ = 12;  // IFBlocks 2 and 3 (80 % of the FLOPs): plain fp16 activations in the residual chain (profiles/r1_precision_study_plain_blocks.txt)
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;
     Net nets_[3];           // flownet, contextnet, fusionnet

@@ -320,7 +320,8 @@ int V46Runner::ensure(int w, int h, int batch, std::string& err) {
     return 0;
 }
 
-int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, int batch, cudaStream_t st) {
+int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, float* out_f32, int oh, int ow, bool out_s2d, int batch, bool split_in,
+                    bool split_out, cudaStream_t st) {
     const Layer& L = net_->layers[li];
     const DeviceWeights& W = wr_->weights(li);
     TcConvArgs a;
@@ -328,22 +329,22 @@ int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, fl
     a.wpk = (const __half*)W.wpk;
     a.bias = W.biasN;
     a.H = oh; a.W = ow; a.Cin = W.cinp; a.Cout = L.geti(0, 0); a.N = W.tcN;
-    a.split_in = 1;
+    a.split_in = split_in;
     a.s2 = W.tc_s2;
     a.num_sms = wr_->num_sms;
     a.batch = batch;
-    a.in_bstride = (size_t)(W.tc_s2 ? 4 : 1) * W.cinp * oh * ow * 2;  // hi + lo planes of one image
+    a.in_bstride = (size_t)(W.tc_s2 ? 4 : 1) * W.cinp * oh * ow * 2;  // room for hi + lo planes of one image (also when only hi is used)
     if (L.type == "Convolution") {
         a.out_bstride = a.res_bstride = (size_t)L.geti(0, 0) * oh * ow * 2;
         a.epi = TC_EPI_C8;
         a.out = out;
         a.out_plane = (size_t)a.Cout * oh * ow;
-        a.split_out = 1;
+        a.split_out = split_out;
         a.out_s2d = out_s2d;
         a.act_mode = 1;
         a.slope = slope_;
         if (L.geti(9, 0) == 2) { const ParamVal* ap = L.get(10); a.slope = ap && !ap->af.empty() ? ap->af[0] : 0.f; }
-        if (res) { a.res = res; a.res_plane = a.out_plane; a.res_split = 1; a.res_mode = 1; }
+        if (res) { a.res = res; a.res_plane = a.out_plane; a.res_split = split_in; a.res_mode = 1; }
     } else {
         a.epi = TC_EPI_DECONV;
         a.out_f32 = out_f32;
@@ -384,15 +385,18 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         else head_kernel<1><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
         const int* L = &conv_[k * 11];
-        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, st);   // 3x3 s2, leaky
-        r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, n, st);     // 3x3 s2, leaky
+        // precision: block-head inputs and the first two convs always carry split (fp32-equivalent) operands; the
+        // residual chain of a block is split unless that block is listed in plain_mask_ (tier 3: plain fp16 there)
+        const bool sp = !((plain_mask_ >> k) & 1);
+        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, true, true, st);   // 3x3 s2, leaky
+        r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, n, true, sp, st);       // 3x3 s2, leaky
         __half* cur = a_[k];
         __half* nxt = b_[k];
-        for (int j = 0; j < 8; j++) {                                                     // y = leaky(conv(y) + y)
-            r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, n, st);
+        for (int j = 0; j < 8; j++) {                                                                 // y = leaky(conv(y) + y)
+            r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, n, sp, sp, st);
             __half* tmp = cur; cur = nxt; nxt = tmp;
         }
-        r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, n, st);       // deconv + PixelShuffle -> flow<k>
+        r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, n, sp, false, st);        // deconv + PixelShuffle -> flow<k>
         if (r) { err = "tensor-core conv launch failed in block " + std::to_string(k); return -3; }
         dim3 gf(cdiv(wp, 128), hp, n);
         if (k == 0) update_kernel<8, true><<<gf, 128, 0, st>>>(d_[0], hk, wk, F_, M_, hp, wp);
