@@ -310,7 +310,7 @@ def main():
     flop = 2.0 * 9 * 64 * 64 * ch * cw  # algorithmic FLOPs of the layer; the hi+lo split issues 2x this on the tensor pipe
     achieved = flop / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md)
-    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else {(272, 480): 17.6e6}.get((ch, cw))
+    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
                 "kernel": "tc_conv3x3_kernel<64,4,3> %dx%d" % (cw, ch), "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
                 "tensor_issue_multiplier": 2 if split else 1}

@@ -134,3 +134,27 @@ def test_v46_fused_fast_path(pkg, w, h):
         ref, _ = parity.run_oracle("rife-v4.6", a, b, 0.5)
         res = parity.compare(fast, ref)
         assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
+
+
+@pytest.mark.parametrize("mask", [0, 12, 15])
+@pytest.mark.parametrize("case", ["synth", "large_motion", "readme_images"])
+def test_v46_precision_choices_stay_within_one_lsb(pkg, mask, case):
+    """plain_blocks: which IFBlocks run their residual chain on plain fp16 activations (default 12 = blocks 2,3).
+    Every choice, including all four blocks, must stay within 1 LSB / 50 dB of the oracle."""
+    _need("rife-v4.6")
+    if case == "synth":
+        a, b = parity.synth.pair(640, 360)
+    elif case == "large_motion":
+        a, b = parity.synth.pair(640, 352, dx=24, dy=16)
+    else:
+        try:
+            from PIL import Image
+            d = os.path.join(parity.REF_DIR, "images")
+            a = np.array(Image.open(os.path.join(d, "0.png")).convert("RGB"))
+            b = np.array(Image.open(os.path.join(d, "1.png")).convert("RGB"))
+        except Exception:
+            pytest.skip("README frames or PIL not available")
+    ref, _ = parity.run_oracle("rife-v4.6", a, b, 0.5)
+    out = parity.run_gpu(pkg, "rife-v4.6", a, b, 0.5, options={"plain_blocks": mask})
+    res = parity.compare(out, ref)
+    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["share_ne"] < 0.02, res
