@@ -298,21 +298,28 @@ def main():
     pmask = eng.get_option("plain_blocks") if eng.get_option("fast_active") else 0
     split = 1 if (args.precision == 1 and not (pmask & 8)) else 0  # block 3's residual chain: plain fp16 when bit 3 is set
     iters = 20
+    # images per launch exactly as in the timed step (the lock-step batch of the fused path; 1 on the generic path)
+    kb = 1
+    if eng.get_option("fast_active"):
+        kb = args.batch if args.batch > 0 else max(1, min(8, (2 * 3840 * 2176) // (hp * wp)))
+        kb = min(kb, PAIRS_PER_STEP)
     with torch.cuda.stream(stream):
-        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, 3, gpuid=local)
+        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, 3, gpuid=local, batch=kb)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, iters, gpuid=local)
+        pkg.bench_conv(stream.cuda_stream, 64, 64, ch, cw, split, iters, gpuid=local, batch=kb)
         e1.record(stream)
         torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / iters
-    flop = 2.0 * 9 * 64 * 64 * ch * cw  # algorithmic FLOPs of the layer; the hi+lo split issues 2x this on the tensor pipe
+    flop = 2.0 * 9 * 64 * 64 * ch * cw * kb  # algorithmic FLOPs per launch; a hi+lo split issues 2x this on the tensor pipe
     achieved = flop / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md)
-    traffic = {(272, 480): 34.4e6, (544, 960): 242.3e6}.get((ch, cw)) if split else None
+    # (single-image captures, scaled by the images per launch: the kernel re-reads nothing across images)
+    traffic = ({(272, 480): 34.4e6, (544, 960): 242.3e6} if split else {(272, 480): 16.9e6, (544, 960): 89.7e6}).get((ch, cw))
+    traffic = traffic * kb if traffic else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
-                "kernel": "tc_conv3x3_kernel<64,4,3> %dx%d" % (cw, ch), "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
+                "kernel": "tc_conv3x3_kernel<64,4,3,9> %d x %dx%d" % (kb, cw, ch), "images_per_launch": kb, "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
                 "tensor_issue_multiplier": 2 if split else 1}
 
     if rank == 0:

@@ -89,6 +89,8 @@ int rife_b200_set_stream(rife_b200_t* handle, void* cuda_stream);
 /* Launches the tcgen05 conv3x3 (cin -> cout, h x w, bias + residual + leaky) `iters` times on `cuda_stream` with
  * device-resident synthetic data and returns; used by bench.py to time the dominant kernel with its own events. */
 int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
+/* same with `batch` images per launch (the lock-step batch of the fused path) */
+int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int batch, int iters);
 
 /* Diagnostics: clock64 timeline (64 slots per CTA) of one tcgen05 conv launch; see csrc/tc_conv.cu for the slot map */
 int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, int split, unsigned long long* host_out,

@@ -306,6 +306,7 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
 }
 
 extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
+extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int batch, int iters);
 
 extern "C" int rife_b200_set_stream(rife_b200_t* h, void* cuda_stream) {
     GUARD_BEGIN
@@ -335,9 +336,14 @@ extern "C" int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h
 }
 
 extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters) {
+    return rife_b200_bench_conv_batched(gpuid, cuda_stream, cin, cout, h, w, split, 1, iters);
+}
+
+extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int batch, int iters) {
     GUARD_BEGIN
     using namespace rife;
-    if (cin % 16 || cout % 16 || cin <= 0 || h <= 0 || w <= 0 || iters <= 0) return RIFE_B200_ERR_ARG;
+    if (cin % 16 || cout % 16 || cin <= 0 || h <= 0 || w <= 0 || iters <= 0 || batch < 1 || batch > 16) return RIFE_B200_ERR_ARG;
+    h *= batch;  // the synthetic tensors below are allocated as one tall image and then addressed as `batch` images
     if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
     struct Cache { int cin = 0, cout = 0, h = 0, w = 0, split = -1; __half *in8 = 0, *out8 = 0, *wpk = 0; float* bias = 0; };
     static Cache c;
@@ -369,6 +375,14 @@ extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int c
     a.res = cin == cout ? c.in8 : nullptr; a.res_plane = (size_t)cin * hw; a.res_split = split; a.res_mode = cin == cout ? 1 : 0;
     a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = cout; a.split_in = split; a.split_out = split; a.epi = TC_EPI_C8; a.act_mode = 1;
     a.dbg = g_dbg_dev;
+    if (batch > 1) {
+        // reinterpret the tall synthetic tensor as `batch` images: per image [planes][C/8][h/batch][w][8]; the values are
+        // arbitrary, only the addressing pattern matters for timing
+        a.H = h / batch;
+        a.batch = batch;
+        a.in_bstride = a.res_bstride = a.out_bstride = (size_t)cin * (h / batch) * w * 2;
+        a.out_plane = a.res_plane = (size_t)cout * (h / batch) * w;
+    }
     for (int i = 0; i < iters; i++) {
         int r = launch_tc_conv(a, c.in8, st);
         if (r) return RIFE_B200_ERR_INTERNAL;
