@@ -6,6 +6,7 @@ import __graft_entry__ as g
 pkg = g.load_package()
 h, w = (272, 480) if len(sys.argv) < 2 or sys.argv[1] == "1080p" else (544, 960)
 split = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 s = torch.cuda.Stream()
-pkg.bench_conv(s.cuda_stream, 64, 64, h, w, split, 4)
+pkg.bench_conv(s.cuda_stream, 64, 64, h, w, split, 4, batch=batch)
 torch.cuda.synchronize()
