@@ -1,9 +1,9 @@
 // fused_v46.cu -- hand-scheduled fast path for the rife-v4.6 IFNet (the BASELINE hot path): the ~50 elementwise
 // graph nodes between the conv stacks (Interp / Crop / BinaryOp / Eltwise / Concat / rife.Warp / Sigmoid, SURVEY.md
-// Appendix B) collapse into four HBM kernels, and every convolution runs on the tcgen05 kernel (tc_conv.cu):
+// Appendix B) collapse into three HBM kernels, and every convolution runs on the tcgen05 kernel (tc_conv.cu):
 //   head0   x0 = bilinear(cat(I0, I1, T), 1/8)                                   -> C8 space-to-depth, split fp16
-//   head<S> x  = cat(bilinear(cat(warp(I0,F01), warp(I1,F23), T, M), 1/S), bilinear(F, 1/S) / S)   (S = 4, 2, 1)
-//   update  U = bilinear(d_k, S); F = F + S*U[0:4] (k = 0: F = S*U[0:4]); M = M + U[4]
+//   head<S> U = bilinear(d_{k-1}, S'); F = F + S'*U[0:4] (k = 1: F = S'*U[0:4]); M = M + U[4]   (the update after block k-1)
+//           x = cat(bilinear(cat(warp(I0,F01), warp(I1,F23), T, M), 1/S), bilinear(F, 1/S) / S)   (S = 4, 2, 1)
 //   tail    F3 = F + d3[0:4]; M3 = M + d3[4]; out = warp(I0,F3_01)*sigmoid(M3) + warp(I1,F3_23)*(1 - sigmoid(M3)) -> u8
 // Arithmetic is the generic executor's, operation for operation (same lin_coeff, H pass then V pass, same warp), so the
 // two paths agree to fp32 rounding; Engine::load() additionally checks the fast path against the generic executor on a
@@ -121,25 +121,92 @@ __global__ void head0_kernel(const float* __restrict__ I0, const float* __restri
     store_c8_s2d_16(out, v, oy, ox, oh, ow);
 }
 
-// block head for k >= 1: flownet.param:50-62 (S = 4), :106-115 (2), :158-165 (1)
-template <int S>
-__global__ void head_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M, TBatch tb,
-                            int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+// Block head for k >= 1 fused with the flow / mask update that follows block k-1
+// (flownet.param:47-62 for k = 1, :99-115 for k = 2, :152-165 for k = 3):
+//   U = bilinear(d_{k-1}, SP);  F = F + SP*U[0:4]  (k = 1: F = SP*U[0:4]);  M = M + U[4]          at full resolution
+//   x = cat(bilinear(cat(warp(I0,F01), warp(I1,F23), T, M), 1/S), bilinear(F, 1/S) / S)          at 1/S resolution
+// One thread owns one output pixel and its S x S full-resolution footprint: it updates (and stores) F, M for the whole
+// footprint and keeps the 2x2 (S > 1) or 1 (S = 1) tap pixels the down-sampling reads -- for these integer scales the
+// taps always lie inside the thread's own footprint, so no other thread's update is needed.
+template <int S, int SP, bool FIRST>
+__global__ void head_update_kernel(const float* __restrict__ I0, const float* __restrict__ I1, float* __restrict__ F, float* __restrict__ M,
+                                   const float* __restrict__ d, int dh, int dw, TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
-    const size_t plane = (size_t)hp * wp;
+    const size_t plane = (size_t)hp * wp, dplane = (size_t)dh * dw;
     const int b = blockIdx.z;
     const float t = tb.t[b];
     I0 += (size_t)b * 3 * plane;
     I1 += (size_t)b * 3 * plane;
     F += (size_t)b * 4 * plane;
     M += (size_t)b * plane;
+    d += (size_t)b * 6 * dplane;
     out += (size_t)b * 16 * oh * ow * 2;
-    float v[16];
-    // 8-channel vector cat(W0, W1, T, M) and the 4 flow channels at one full-resolution pixel
-    auto at = [&](int y, int x, float* e) {
-        const size_t pi = (size_t)y * wp + x;
-        const float f0 = F[pi], f1 = F[plane + pi], f2 = F[2 * plane + pi], f3 = F[3 * plane + pi];
+    constexpr int T0 = S == 1 ? 0 : S / 2 - 1;  // first tap inside the footprint (S = 4: 1, S = 2: 0)
+    constexpr int NT = S == 1 ? 1 : 2;
+    float tapF[NT][NT][4], tapM[NT][NT];
+    // horizontal up-sampling coefficients of the S footprint columns (shared by all rows)
+    int usx[S];
+    float ua0[S], ua1[S];
+#pragma unroll
+    for (int fx = 0; fx < S; fx++) {
+        float f;
+        lin_coeff(S * ox + fx, dw, wp, usx[fx], f);
+        ua0[fx] = 1.f - f;
+        ua1[fx] = f;
+    }
+#pragma unroll
+    for (int fy = 0; fy < S; fy++) {
+        const int y = S * oy + fy;
+        int usy;
+        float f;
+        lin_coeff(y, dh, hp, usy, f);
+        const float ub0 = 1.f - f, ub1 = f;
+        float nf[4][S], nm[S];
+        const size_t p0 = (size_t)y * wp + S * ox;  // first footprint pixel of this row: S consecutive floats per plane
+        // vectorised row access: S floats = one 16-byte (S = 4) / 8-byte (S = 2) / 4-byte transaction per plane
+        auto load_row = [&](const float* base, float* dst) {
+            if constexpr (S == 4) { float4 q = *reinterpret_cast<const float4*>(base + p0); dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w; }
+            else if constexpr (S == 2) { float2 q = *reinterpret_cast<const float2*>(base + p0); dst[0] = q.x; dst[1] = q.y; }
+            else dst[0] = base[p0];
+        };
+        auto store_row = [&](float* base, const float* src) {
+            if constexpr (S == 4) *reinterpret_cast<float4*>(base + p0) = make_float4(src[0], src[1], src[2], src[3]);
+            else if constexpr (S == 2) *reinterpret_cast<float2*>(base + p0) = make_float2(src[0], src[1]);
+            else base[p0] = src[0];
+        };
+        float oldf[4][S], oldm[S];
+        if (!FIRST) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) load_row(F + c * plane, oldf[c]);
+            load_row(M, oldm);
+        }
+#pragma unroll
+        for (int fx = 0; fx < S; fx++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float u = bilerp(d + c * dplane, dw, usy, usx[fx], ua0[fx], ua1[fx], ub0, ub1);
+                nf[c][fx] = FIRST ? u * (float)SP : oldf[c][fx] * 1.f + u * (float)SP;  // BinaryOp mul | Eltwise SUM {1, SP}
+            }
+            const float um = bilerp(d + 4 * dplane, dw, usy, usx[fx], ua0[fx], ua1[fx], ub0, ub1);
+            nm[fx] = FIRST ? um : oldm[fx] + um;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) store_row(F + c * plane, nf[c]);
+        store_row(M, nm);
+#pragma unroll
+        for (int fx = 0; fx < S; fx++) {
+            if (fy >= T0 && fy < T0 + NT && fx >= T0 && fx < T0 + NT) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) tapF[fy - T0][fx - T0][c] = nf[c][fx];
+                tapM[fy - T0][fx - T0] = nm[fx];
+            }
+        }
+    }
+    // 8-channel vector cat(W0, W1, T, M) and the 4 flow channels at one full-resolution tap pixel
+    auto at = [&](int ty, int tx, float* e) {
+        const int y = S * oy + T0 + ty, x = S * ox + T0 + tx;
+        const float f0 = tapF[ty][tx][0], f1 = tapF[ty][tx][1], f2 = tapF[ty][tx][2], f3 = tapF[ty][tx][3];
         WarpTap t0 = warp_tap(x, y, f0, f1, wp, hp);
         WarpTap t1 = warp_tap(x, y, f2, f3, wp, hp);
 #pragma unroll
@@ -148,26 +215,27 @@ __global__ void head_kernel(const float* __restrict__ I0, const float* __restric
             e[3 + c] = warp_sample(I1 + c * plane, t1);
         }
         e[6] = t;
-        e[7] = M[pi];
+        e[7] = tapM[ty][tx];
         e[8] = f0; e[9] = f1; e[10] = f2; e[11] = f3;
     };
+    float v[16];
     if (S == 1) {
         // Interp at identical size returns its input untouched (interp.cpp), then Concat
         float e[12];
-        at(oy, ox, e);
+        at(0, 0, e);
 #pragma unroll
         for (int c = 0; c < 12; c++) v[c] = e[c];
     } else {
         int sx, sy;
         float fx, fy;
-        lin_coeff(ox, wp, ow, sx, fx);
+        lin_coeff(ox, wp, ow, sx, fx);  // == S*ox + T0 for these scales; kept for the exact coefficient arithmetic
         lin_coeff(oy, hp, oh, sy, fy);
         const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
         float e00[12], e01[12], e10[12], e11[12];
-        at(sy, sx, e00);
-        at(sy, sx + 1, e01);
-        at(sy + 1, sx, e10);
-        at(sy + 1, sx + 1, e11);
+        at(0, 0, e00);
+        at(0, NT - 1, e01);
+        at(NT - 1, 0, e10);
+        at(NT - 1, NT - 1, e11);
 #pragma unroll
         for (int c = 0; c < 12; c++) {
             float row0 = e00[c] * a0 + e01[c] * a1;
@@ -180,31 +248,6 @@ __global__ void head_kernel(const float* __restrict__ I0, const float* __restric
 #pragma unroll
     for (int c = 12; c < 16; c++) v[c] = 0.f;
     store_c8_s2d_16(out, v, oy, ox, oh, ow);
-}
-
-// flow / mask update after block k: flownet.param:47-50,58 (k = 0), :99-105 (k = 1), :152-158 (k = 2)
-template <int S, bool FIRST>
-__global__ void update_kernel(const float* __restrict__ d, int dh, int dw, float* __restrict__ F, float* __restrict__ M, int hp, int wp) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= wp) return;
-    d += (size_t)blockIdx.z * 6 * dh * dw;
-    F += (size_t)blockIdx.z * 4 * hp * wp;
-    M += (size_t)blockIdx.z * hp * wp;
-    int sx, sy;
-    float fx, fy;
-    lin_coeff(x, dw, wp, sx, fx);
-    lin_coeff(y, dh, hp, sy, fy);
-    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const size_t dplane = (size_t)dh * dw, plane = (size_t)hp * wp, pi = (size_t)y * wp + x;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        float u = bilerp(d + c * dplane, dw, sy, sx, a0, a1, b0, b1);
-        if (FIRST) F[c * plane + pi] = u * (float)S;                         // BinaryOp mul by scalar
-        else F[c * plane + pi] = F[c * plane + pi] * 1.f + u * (float)S;     // Eltwise SUM, coeffs {1, S}
-    }
-    float um = bilerp(d + 4 * dplane, dw, sy, sx, a0, a1, b0, b1);
-    if (FIRST) M[pi] = um;
-    else M[pi] = M[pi] + um;
 }
 
 // last update + blend + rife_postproc: flownet.param:202-217, src/rife.cpp:4375-4398, mat_pixel.cpp:158
@@ -379,10 +422,11 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
     for (int k = 0; k < 4; k++) {
         const int hk = hp / S[k], wk = wp / S[k];
         dim3 g(cdiv(wk, 128), hk, n);
+        // head of block k, fused with the flow / mask update that follows block k-1
         if (k == 0) head0_kernel<<<g, 128, 0, st>>>(I0_, I1_, tb, hp, wp, hk, wk, x_[0]);
-        else if (k == 1) head_kernel<4><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[1]);
-        else if (k == 2) head_kernel<2><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[2]);
-        else head_kernel<1><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, tb, hp, wp, hk, wk, x_[3]);
+        else if (k == 1) head_update_kernel<4, 8, true><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[1]);
+        else if (k == 2) head_update_kernel<2, 4, false><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[1], hp / 4, wp / 4, tb, hp, wp, hk, wk, x_[2]);
+        else head_update_kernel<1, 2, false><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[2], hp / 2, wp / 2, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
         const int* L = &conv_[k * 11];
         // precision: block-head inputs and the first two convs always carry split (fp32-equivalent) operands; the
@@ -398,11 +442,6 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         }
         r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, n, sp, false, st);        // deconv + PixelShuffle -> flow<k>
         if (r) { err = "tensor-core conv launch failed in block " + std::to_string(k); return -3; }
-        dim3 gf(cdiv(wp, 128), hp, n);
-        if (k == 0) update_kernel<8, true><<<gf, 128, 0, st>>>(d_[0], hk, wk, F_, M_, hp, wp);
-        else if (k == 1) update_kernel<4, false><<<gf, 128, 0, st>>>(d_[1], hk, wk, F_, M_, hp, wp);
-        else if (k == 2) update_kernel<2, false><<<gf, 128, 0, st>>>(d_[2], hk, wk, F_, M_, hp, wp);
-        if (k < 3) g_launch_count++;
     }
     tail_kernel<<<dim3(cdiv(w, 128), h, n), 128, 0, st>>>(I0_, I1_, F_, M_, d_[3], hp, wp, ob, w, h);
     g_launch_count++;

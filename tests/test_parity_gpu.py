@@ -158,3 +158,53 @@ def test_v46_precision_choices_stay_within_one_lsb(pkg, mask, case):
     out = parity.run_gpu(pkg, "rife-v4.6", a, b, 0.5, options={"plain_blocks": mask})
     res = parity.compare(out, ref)
     assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["share_ne"] < 0.02, res
+
+
+def test_concurrent_process_calls_on_one_handle(pkg):
+    """The reference calls RIFE::process from several proc threads on one object (src/main.cpp:346-366)."""
+    _need("rife-v4.6")
+    import threading
+    w, h = 320, 192
+    frames = [parity.synth.frame(k, w, h) for k in range(5)]
+    v2, v4 = pkg.family_flags("rife-v4.6")
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir("rife-v4.6"))
+    expect = [r.process(frames[i], frames[i + 1], 0.5) for i in range(4)]
+    got = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = r.process(frames[i], frames[i + 1], 0.5)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    r.close()
+    assert not errs, errs
+    for e, g_ in zip(expect, got):
+        assert np.array_equal(e, g_)
+
+
+def test_batched_lockstep_equals_single_pair_path(pkg):
+    """8 pairs in one lock-step batch (TMA 4D tensor maps, blockIdx.z image index) vs the same pairs one at a time."""
+    _need("rife-v4.6")
+    w, h = 256, 160
+    frames = [parity.synth.frame(k, w, h, dx=5, dy=3) for k in range(9)]
+    v2, v4 = pkg.family_flags("rife-v4.6")
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir("rife-v4.6"))
+    r.set_option("lanes", 1)
+    singles = [r.process(frames[i], frames[i + 1], 0.25 + 0.0625 * i) for i in range(8)]
+    outs = [np.empty_like(frames[0]) for _ in range(8)]
+    r.set_option("batch", 8)
+    r.process_batch_ptr([f.ctypes.data for f in frames[:8]], [f.ctypes.data for f in frames[1:]], w, h, [0.25 + 0.0625 * i for i in range(8)],
+                        [o.ctypes.data for o in outs])
+    r.close()
+    for s_, o in zip(singles, outs):
+        assert np.array_equal(s_, o)

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_1080p_plain_b8 python tools/profile_tc.py 1080p 0 8 > gpurun_out/ncu_tc_stdout.txt 2>&1)
-(timeout 300 ncu --set full --clock-control none -k regex:tc_conv3x3 -s 2 -c 1 -o gpurun_out/prof_tc_conv64_4k_plain_b2 python tools/profile_tc.py 4k 0 2 >> gpurun_out/ncu_tc_stdout.txt 2>&1)
-# launch list of one batched step (8 pairs, 1 lane) at 1080p
-RIFE_BENCH_PAIRS=8 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_1080p_batched.csv python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline > gpurun_out/ncu_bench_stdout.txt 2>&1
-wc -l gpurun_out/launches_1080p_batched.csv
-ls -la gpurun_out/*.ncu-rep
+(timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -q -x 2>&1 | tail -6) > gpurun_out/parity_tests.txt
+tail -4 gpurun_out/parity_tests.txt
+(timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_1080p_default.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_1080p_default.txt'));print('1080p',round(d['value'],1),round(d['e2e']['value'],1),d['gpu_launches'])"
+(timeout 300 python bench.py --steps 3 --warmup 3 --workload 4k --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_4k_default.txt
+python -c "import json;d=json.load(open('gpurun_out/bench_4k_default.txt'));print('4k',round(d['value'],1),round(d['e2e']['value'],1))"
