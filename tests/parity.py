@@ -25,6 +25,10 @@ def model_dir(name):
     d = os.path.join(ROOT, "tests", "models", name)  # synthetic-weight models (tests/make_synth_model.py)
     if os.path.isdir(d):
         return d
+    if name == "rife-v4.6":
+        # the reference's model files did not travel: same architecture, seeded random weights (git-ignored, regenerated on demand)
+        import make_synth_model
+        return make_synth_model.write_model(d, seed=0)
     return None
 
 

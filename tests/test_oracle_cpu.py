@@ -50,3 +50,28 @@ def test_reference_binary_reproduces_golden(name):
     out, _ = parity.run_oracle(m["model"], a, b, which="ref", **m["oracle_kwargs"])
     res = parity.compare(out, ARRAYS[name])
     assert res["max_abs_diff"] <= 1 and res["share_ne"] < 2e-3, res
+
+
+def test_synthetic_model_loads_in_both_oracles(tmp_path):
+    """tests/make_synth_model.py writes the rife-v4.6 architecture in the reference's file format: the reference binary
+    (real ncnn parser) must accept it and agree with the restatement."""
+    import make_synth_model
+    import subprocess
+    d = make_synth_model.write_model(str(tmp_path / "rife-v4.6"), seed=1)
+    assert os.path.getsize(os.path.join(d, "flownet.bin")) == 10614320  # same byte count as the reference's file
+    a, b = parity.synth.pair(96, 64)
+    (tmp_path / "a.rgb").write_bytes(a.tobytes())
+    (tmp_path / "b.rgb").write_bytes(b.tobytes())
+    outs = []
+    for exe in (parity.ref_binary(), parity.port_binary()):
+        if exe is None:
+            continue
+        o = str(tmp_path / ("o%d.rgb" % len(outs)))
+        subprocess.run([exe, "--model", d, "--family", "v4", "--w", "96", "--h", "64", "--in0", str(tmp_path / "a.rgb"), "--in1", str(tmp_path / "b.rgb"),
+                        "--out", o, "--threads", "4"], check=True, stdout=subprocess.PIPE)
+        outs.append(np.fromfile(o, np.uint8))
+    if len(outs) < 1:
+        pytest.skip("no oracle executable")
+    assert outs[0].std() > 5
+    if len(outs) == 2:
+        assert np.abs(outs[0].astype(int) - outs[1].astype(int)).max() <= 1
