@@ -393,6 +393,7 @@ int V46Runner::conv(int li, const __half* in, __half* out, const __half* res, fl
         a.out_f32 = out_f32;
         a.ocs = W.ocs;
         a.ps = 2;
+        a.out_planes = 5;  // flow (4) + mask (1); the 6th PixelShuffle plane is never read by head / tail
         a.outf_bstride = (size_t)6 * (oh * 4) * (ow * 4);
     }
     return launch_tc_conv(a, in, st);
@@ -429,8 +430,10 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         else head_update_kernel<1, 2, false><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[2], hp / 2, wp / 2, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
         const int* L = &conv_[k * 11];
-        // precision: block-head inputs and the first two convs always carry split (fp32-equivalent) operands; the
-        // residual chain of a block is split unless that block is listed in plain_mask_ (tier 3: plain fp16 there)
+        // precision: the block-head tensor and the two stride-2 convs that follow it always run on split (fp32-equivalent)
+        // operands -- measured: making conv0's output / conv1's input plain fp16 doubles the 1-LSB flips and, with all four
+        // blocks plain, produces 4-LSB errors on the README frames; the residual chain and the deconv of a block are split
+        // unless the block is listed in plain_mask_ (plain fp16 activations there)
         const bool sp = !((plain_mask_ >> k) & 1);
         int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, true, true, st);   // 3x3 s2, leaky
         r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, n, true, sp, st);       // 3x3 s2, leaky

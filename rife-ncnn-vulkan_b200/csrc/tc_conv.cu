@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                         if (r_ == 2) {
 #pragma unroll
                             for (int oc4 = 0; oc4 < OCS / 4; oc4++) {  // oc4 = qq
-                                if (oc4 * 4 >= a.Cout) break;
+                                if (oc4 * 4 >= a.Cout || (a.out_planes > 0 && oc4 >= a.out_planes)) break;
 #pragma unroll
                                 for (int sh = 0; sh < 2; sh++) {
                                     const int o0 = oc4 * 4 + sh * 2;  // oc for sw = 0

@@ -26,6 +26,7 @@ struct TcConvArgs {
     int res_mode;           // 0 none, 1 add before activation, 2 add after activation
     int act_mode;           // 0 none, 1 leaky(slope), 2 prelu, 3 sigmoid (deconv epilogue only)
     int ocs, ps;            // deconv: output-channel slots per parity, PixelShuffle factor (1 = none)
+    int out_planes;         // deconv + PixelShuffle: store only the first out_planes planes (0 = all)
     int batch;              // images per launch (0 / 1 = single); image b lives at base + b * *_bstride
     size_t in_bstride, res_bstride, out_bstride, outf_bstride;  // elements of the respective tensors
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
