@@ -92,13 +92,16 @@ int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h,
 /* same with `batch` images per launch (the lock-step batch of the fused path) */
 int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int batch, int iters);
 
-/* Diagnostics: clock64 timeline (64 slots per CTA) of one tcgen05 conv launch; see csrc/tc_conv.cu for the slot map */
+/* Diagnostics: clock64 timeline (64 slots per CTA) of one tcgen05 conv launch; see csrc/tc_conv.cu for the slot map.
+ * `split`: bit 0 = split hi+lo operands, bits 8-15 = images per launch (0 = 1), bits 16-23 = tiles each CTA skips
+ * before recording (steady state instead of pipeline fill). */
 int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, int split, unsigned long long* host_out,
                                   int max_ctas);
 
 /* Diagnostics: runs ONE convolution layer through the tcgen05 tensor-core kernel and through the fp32 CUDA-core
  * kernel on the same data and returns both results (planar fp32, host memory) so a test can compare them.
- * mode 0: conv3x3 s1 p1 (+bias, + optional residual `res`, + leaky `slope`), in [cin][h][w] -> out [cout][h][w]
+ * mode 0: conv3x3 s1 p1 (+bias, + optional residual `res`, + leaky `slope`), in [cin][h][w] -> out [cout][h][w];
+ *         res == in (same pointer, cin == cout) exercises the self-residual path (identity tap on the tensor core)
  * mode 1: deconv4x4 s2 p1 (+bias) followed by PixelShuffle(ps), in [cin][h][w] -> out [cout/(ps*ps)][2h*ps][2w*ps]
  * split != 0 stores activations as split-fp16 (hi+lo) for the tensor-core path. */
 int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w, int split, int ps, const float* in,

@@ -244,7 +244,8 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     cudaMemcpy(d_biasN, biasN.data(), N * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_wpk, wpk.data(), wpk.size() * 2, cudaMemcpyHostToDevice);
     cudaMemset(d_out_tc, 0, out_elems * 4);
-    if (res) {
+    const bool self_res = res == in && cin == cout && mode == 0;  // residual = the conv's own input (identity-tap path of the kernel)
+    if (res && !self_res) {
         cudaMalloc(&d_res, cout * hw * 4); cudaMalloc(&d_res8, (size_t)cout * hw * 2 * 2);
         cudaMemcpy(d_res, res, cout * hw * 4, cudaMemcpyHostToDevice);
         launch_planar_to_c8(d_res, d_res8, cout, h, w, split, st);
@@ -252,10 +253,10 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     launch_planar_to_c8(d_in, d_in8, cin, h, w, split, st);
     // the reference result uses exactly the values the tensor path sees (hi+lo reconstruction of the input)
     launch_c8_to_planar(d_in8, d_in, cin, h, w, split, st);
-    if (res) launch_c8_to_planar(d_res8, d_res, cout, h, w, split, st);
+    if (res && !self_res) launch_c8_to_planar(d_res8, d_res, cout, h, w, split, st);
     TcConvArgs a;
     memset(&a, 0, sizeof a);
-    a.wpk = d_wpk; a.bias = d_biasN; a.res = d_res8; a.res_plane = (size_t)cout * hw; a.res_split = split;
+    a.wpk = d_wpk; a.bias = d_biasN; a.res = self_res ? d_in8 : d_res8; a.res_plane = (size_t)cout * hw; a.res_split = split;
     a.out = d_out8; a.out_plane = (size_t)cout * hw; a.out_f32 = d_out_tc; a.slope = slope;
     a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = N; a.split_in = split; a.split_out = split;
     a.epi = mode == 0 ? TC_EPI_C8 : TC_EPI_DECONV;
@@ -286,7 +287,7 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
         c.in = d_in; c.wT = d_wT; c.bias = d_bias; c.Cin = cin; c.H = h; c.W = w; c.Cout = cout; c.ocpad = ocpad;
         if (mode == 0) {
             c.out = d_out_ref; c.OH = h; c.OW = w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 1; c.nparity = 1;
-            c.res = d_res; c.post_act = 2; c.post_p0 = slope;
+            c.res = self_res ? d_in : d_res; c.post_act = 2; c.post_p0 = slope;
             launch_conv(c, 3, 1, st);
         } else {
             c.out = d_tmp; c.OH = 2 * h; c.OW = 2 * w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 2; c.nparity = 4;
@@ -317,6 +318,7 @@ extern "C" int rife_b200_set_stream(rife_b200_t* h, void* cuda_stream) {
 }
 
 static unsigned long long* g_dbg_dev = nullptr;
+static int g_dbg_skip = 0, g_dbg_flags = 0;
 
 // diagnostics: per-CTA clock64 timeline of one tcgen05 conv launch (64 slots per CTA, see tc_conv.cu)
 extern "C" int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, int split, unsigned long long* host_out, int max_ctas) {
@@ -326,11 +328,17 @@ extern "C" int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h
     size_t bytes = (size_t)max_ctas * 64 * 8;
     cudaMalloc(&g_dbg_dev, bytes);
     cudaMemset(g_dbg_dev, 0, bytes);
-    int r = rife_b200_bench_conv(gpuid, nullptr, cin, cout, h, w, split, 3);  // warm (dbg active on every launch; last one kept)
+    // split: bit 0 = split operands, bits 8-15 = images per launch (0 -> 1), bits 16-23 = tiles to skip before recording
+    const int batch = ((split >> 8) & 0xff) ? ((split >> 8) & 0xff) : 1;
+    g_dbg_skip = (split >> 16) & 0xff;
+    g_dbg_flags = (split >> 24) & 0x7f;  // epilogue knock-outs, see TcConvArgs::dbg_flags
+    int r = rife_b200_bench_conv_batched(gpuid, nullptr, cin, cout, h, w, split & 1, batch, 3);  // warm (dbg active on every launch; last one kept)
     cudaDeviceSynchronize();
     cudaMemcpy(host_out, g_dbg_dev, bytes, cudaMemcpyDeviceToHost);
     cudaFree(g_dbg_dev);
     g_dbg_dev = nullptr;
+    g_dbg_skip = 0;
+    g_dbg_flags = 0;
     return r;
     GUARD_END
 }
@@ -375,6 +383,8 @@ extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int ci
     a.res = cin == cout ? c.in8 : nullptr; a.res_plane = (size_t)cin * hw; a.res_split = split; a.res_mode = cin == cout ? 1 : 0;
     a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = cout; a.split_in = split; a.split_out = split; a.epi = TC_EPI_C8; a.act_mode = 1;
     a.dbg = g_dbg_dev;
+    a.dbg_skip = g_dbg_skip;
+    a.dbg_flags = g_dbg_flags;
     if (batch > 1) {
         // reinterpret the tall synthetic tensor as `batch` images: per image [planes][C/8][h/batch][w][8]; the values are
         // arbitrary, only the addressing pattern matters for timing

@@ -18,6 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "tc_conv.h"
 #include "kernels.h"
@@ -127,7 +130,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+        "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld variants that name the destination registers as in/out operands: values read after the wait formally depend
+// on it, so the compiler cannot schedule a consumer of an in-flight tcgen05.ld above the wait (software-pipelined loads)
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                   "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -161,14 +192,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
-    float* slope_s = bias_s + N;
+    float* slope_s = reinterpret_cast<float*>(tmem_slot + 4);  // per-channel (slope - 1), PReLU epilogue only
+    // Constant MMA operands, built once per CTA:
+    //  ones  : A tile 128 x 16 with K columns 0..2 = 1      }  first MMA of every tile: D = ones * biasB = the fp32 bias
+    //  biasB : B tile 16 x N, K rows 0..2 = bias as hi+lo+lo2 }  (three fp16 pieces), so no epilogue touches the bias
+    //  ident : res_mode 3 (residual == this conv's own input): the residual is added by the tensor core as a tenth tap
+    //          whose B operand is an identity slice.  K-major matrix of IROWS rows with ones at rows N-16 .. N-1 (row
+    //          N-16+k has its one in K column k); the B view of K chunk kc starts (N-16-16*kc) rows in, which puts the
+    //          ones at columns n = 16*kc + k.  The centre view of the halo tile is the A operand: no global residual read.
+    constexpr int IROWS = 2 * N - 16;
+    __half* ones = reinterpret_cast<__half*>(smem + (size_t)STAGES * stage_bytes + 1024 + 256 + N * sizeof(float));
+    __half* biasB = ones + 2 * 128 * 8;
+    __half* ident = biasB + 2 * N * 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_img = a.tiles_x * a.tiles_y;
     const int ntiles = tiles_img * a.batch;  // image-major: tile -> (image, ty, tx)
     const int KCP = a.Cin / 16;                    // K chunks per parity sub-image (all of them for stride 1)
     const int KC = TAPS == 9 ? KCP : 4 * KCP;
+    const uint32_t dskip = (uint32_t)(a.dbg_skip * KC);  // diagnostics: first recorded pipeline iteration
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -180,10 +222,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < N; i += NTHREADS) {
-        bias_s[i] = a.bias[i];
+    for (int i = threadIdx.x; i < N; i += NTHREADS)
         slope_s[i] = (a.act_mode == 1 ? a.slope : ((a.act_mode == 2 && i < a.Cout) ? a.prelu[i] : 1.f)) - 1.f;  // stored as slope - 1
+    for (int i = threadIdx.x; i < 2 * 128 * 8; i += NTHREADS) ones[i] = __float2half_rn((i < 128 * 8 && (i & 7) < 3) ? 1.f : 0.f);
+    for (int i = threadIdx.x; i < 2 * N; i += NTHREADS) {
+        const int n = i % N, hf = i / N;
+        uint4 z = make_uint4(0, 0, 0, 0);
+        if (hf == 0) {
+            const float b = a.bias[n];
+            const __half h0 = __float2half_rn(b);
+            const float r1 = b - __half2float(h0);
+            const __half h1 = __float2half_rn(r1);
+            const __half h2 = __float2half_rn(r1 - __half2float(h1));
+            z.x = pack2(h0, h1);
+            z.y = pack2(h2, __float2half_rn(0.f));
+        }
+        *reinterpret_cast<uint4*>(biasB + (size_t)i * 8) = z;
     }
+    if (a.res_mode == 3) {
+        for (int i = threadIdx.x; i < 2 * IROWS * 8; i += NTHREADS) {
+            const int j = i & 7, r = (i >> 3) % IROWS, hf = (i >> 3) / IROWS;
+            ident[i] = __float2half_rn(r - (N - 16) == hf * 8 + j ? 1.f : 0.f);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -213,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     for (int p = 0; p < nplanes; p++)
                         tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc, bimg);
                     bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
-                    if (dbg && it < 12) dbg[1 + it] = clock64();
+                    if (dbg && it - dskip < 12u) dbg[1 + it - dskip] = clock64();
                 }
             }
         }
@@ -232,16 +294,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 mbar_wait(&acc_empty[buf], aph ^ 1);
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + buf * ACC_COLS;
+                {   // accumulator := bias (see `ones` / `biasB`)
+                    const uint32_t o_lo = (smem_u32(ones) >> 4) | (((uint32_t)(128 * 16) >> 4) << 16);
+                    const uint32_t bb_lo = (smem_u32(biasB) >> 4) | B_LBO;
+#pragma unroll
+                    for (int m = 0; m < MT; m++) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);
+                }
                 for (int kc = 0; kc < KC; kc++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    if (dbg && it < 12 && lane == 0) dbg[16 + it] = clock64();
+                    if (dbg && it - dskip < 12u && lane == 0) dbg[16 + it - dskip] = clock64();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_base = (st >> 4) | A_LBO;
                     const uint32_t b_base = ((st + nplanes * A_PLANE) >> 4) | B_LBO;
-                    const uint32_t nz = kc != 0;
                     constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
                     if constexpr (TAPS == 9) {
 #pragma unroll
@@ -249,8 +316,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t b_lo = b_base + (uint32_t)(tap * (2 * N * 16) >> 4);
                             const uint32_t a_lo = a_base + (uint32_t)(((dy * TWP + dx) * 16) >> 4);
-                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
-                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, tap == 0 ? nz : 1u);
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                        }
+                        if (a.res_mode == 3) {
+                            constexpr uint32_t I_LBO = ((uint32_t)(IROWS * 16) >> 4) << 16;
+                            const uint32_t b_lo = ((smem_u32(ident) + (uint32_t)((N - 16 - 16 * kc) * 16)) >> 4) | I_LBO;
+                            const uint32_t a_lo = a_base + (uint32_t)(((1 * TWP + 1) * 16) >> 4);
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                         }
                     } else {
                         const int par = kc / KCP, py = par >> 1, px = par & 1;
@@ -264,12 +338,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 const int oy = py ? iy : 1, ox = px ? ix : 1;
                                 const uint32_t b_lo = b_base + (uint32_t)((iy * 2 + ix) * (2 * N * 16) >> 4);
                                 const uint32_t a_lo = a_base + (uint32_t)(((oy * TWP + ox) * 16) >> 4);
-                                if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
-                                else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, (iy | ix) == 0 ? nz : 1u);
+                                if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                                else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                             }
                     }
                     umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
-                    if (dbg && it < 12 && lane == 0) dbg[32 + it] = clock64();
+                    if (dbg && it - dskip < 12u && lane == 0) dbg[32 + it - dskip] = clock64();
                 }
                 umma_commit_elect(&acc_full[buf]);
             }
@@ -298,7 +372,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             __half* out_b = a.out + (size_t)bimg * a.out_bstride;
             float* outf_b = a.out_f32 + (size_t)bimg * a.outf_bstride;
             const bool xvalid = xr < TVALID && x < a.W;
-            if (a.epi == TC_EPI_C8) {
+            if (a.epi == TC_EPI_C8 && (a.res_mode == 0 || a.res_mode == 3) && a.act_mode != 2) {
+                // No residual to fetch (none, or already added by the identity tap), bias already in the accumulator,
+                // one slope for all channels: v = leaky(acc) on packed fp32 pairs, nothing but registers between the TMEM
+                // load and the store.  Loads are software pipelined one block (CBL channels x 32 positions) ahead.
+                constexpr int CBL = (N % 32 == 0) ? 32 : 16;
+                constexpr int NCBL = N / CBL, NBLKL = MT * NCBL;
+                const float sm1 = a.act_mode == 1 ? a.slope - 1.f : 0.f;
+                const float2 sm1v = make_float2(sm1, sm1);
+                // per-thread output address pieces: block (m, cb) -> obase + m * mstep + cb * cbstep
+                const bool s2d = a.out_s2d != 0;
+                const int yb = y0 + yrow;  // row of accumulator 0; accumulator m is two rows further down each
+                const size_t cg_stride = !s2d ? HW : (HW >> 2);
+                const size_t pix0 = !s2d ? (size_t)yb * a.W + x : (size_t)(yb >> 1) * (a.W >> 1) + (x >> 1);
+                const size_t cg_base = !s2d ? 0 : (size_t)((yb & 1) * 2 + (x & 1)) * (a.Cout / 8);
+                __half* const obase = out_b + (cg_base * cg_stride + pix0) * 8;
+                const size_t mstep = (!s2d ? (size_t)2 * a.W : (size_t)(a.W >> 1)) * 8;
+                const size_t cbstep = (size_t)(CBL / 8) * cg_stride * 8, gstep = cg_stride * 8;
+                auto ldblk = [&](int blk, uint32_t* r) {
+                    const int m = blk / NCBL, cb = blk - m * NCBL;
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N + cb * CBL;
+                    if constexpr (CBL == 32) tmem_ld32(trow, r);
+                    else tmem_ld16(trow, r);
+                };
+                auto waitblk = [&](uint32_t* r) {
+                    if constexpr (CBL == 32) tmem_ld_wait_dep32(r);
+                    else tmem_ld_wait_dep16(r);
+                };
+                auto stblk = [&](int blk, const uint32_t* r, auto split_tag) {
+                    constexpr bool SPLIT = decltype(split_tag)::value;
+                    const int m = blk / NCBL, cb = blk - m * NCBL;
+                    if (!(xvalid && yb + 2 * m < a.H)) return;
+                    __half* op = obase + m * mstep + cb * cbstep;
+#pragma unroll
+                    for (int g = 0; g < CBL / 8; g++) {
+                        uint32_t hw_[4], lw_[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            float2 v = make_float2(__uint_as_float(r[g * 8 + 2 * k]), __uint_as_float(r[g * 8 + 2 * k + 1]));
+                            // leaky / identity: v*s for v < 0  ==  v + min(v,0)*(s-1)
+                            v = __ffma2_rn(make_float2(fminf(v.x, 0.f), fminf(v.y, 0.f)), sm1v, v);
+                            const __half2 h = __float22half2_rn(v);
+                            hw_[k] = *reinterpret_cast<const uint32_t*>(&h);
+                            if constexpr (SPLIT) {
+                                const float2 f = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(v.x - f.x, v.y - f.y);
+                                lw_[k] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(op + g * gstep) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
+                        if constexpr (SPLIT) *reinterpret_cast<uint4*>(op + a.out_plane + g * gstep) = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+                    }
+                };
+                auto stsel = [&](int blk, const uint32_t* r) {
+                    if (a.split_out) stblk(blk, r, std::true_type{});
+                    else stblk(blk, r, std::false_type{});
+                };
+                uint32_t ra[CBL], rb[CBL];
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
+                if (dbg && warp == 2 && lane == 0 && tcount - (uint32_t)a.dbg_skip < 4u) dbg[44 + 2 * (tcount - a.dbg_skip)] = clock64();
+                if (ehalf < NBLKL && !(a.dbg_flags & 8)) {
+                    ldblk(ehalf, ra);
+#pragma unroll 1
+                    for (int blk = ehalf; blk < NBLKL; blk += 4) {
+                        waitblk(ra);
+                        if (blk + 2 < NBLKL) ldblk(blk + 2, rb);
+                        stsel(blk, ra);
+                        if (blk + 2 < NBLKL) {
+                            waitblk(rb);
+                            if (blk + 4 < NBLKL) ldblk(blk + 4, ra);
+                            stsel(blk + 2, rb);
+                        }
+                    }
+                }
+            } else if (a.epi == TC_EPI_C8) {
                 // v = act(acc + bias + m1*res) + m2*res with per-channel slopes from shared memory: one branch-free body
                 // for every (residual, leaky / PReLU / none) combination keeps the unrolled code small (an earlier, fully
                 // unrolled and flag-branchy version was 215 KB of SASS and instruction-fetch bound).
@@ -333,13 +481,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             for (int g2 = 0; g2 < 2; g2++) {
                                 const int gl = c * 2 + g2;   // group inside the block
                                 const int cg = cb * G + gl;  // global 8-channel group
-                                const float4 bA = *reinterpret_cast<const float4*>(bias_s + cg * 8), bB = *reinterpret_cast<const float4*>(bias_s + cg * 8 + 4);
                                 const float4 sA = *reinterpret_cast<const float4*>(slope_s + cg * 8), sB = *reinterpret_cast<const float4*>(slope_s + cg * 8 + 4);
-                                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
                                 const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};  // slope - 1
                                 float v[8], rr[8];
 #pragma unroll
-                                for (int j = 0; j < 8; j++) { v[j] = __uint_as_float(r[g2 * 8 + j]) + bb[j]; rr[j] = 0.f; }
+                                for (int j = 0; j < 8; j++) { v[j] = __uint_as_float(r[g2 * 8 + j]); rr[j] = 0.f; }  // bias: already in the accumulator
                                 if (has_res) {
                                     const __half2* hh = reinterpret_cast<const __half2*>(&rcur[gl]);
 #pragma unroll
@@ -384,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 if (ehalf < NBLK) prefetch(ehalf, rb0);
                 mbar_wait(&acc_full[buf], aph);
                 tc_fence_after();
-                if (dbg && warp == 2 && lane == 0 && tcount < 4) dbg[44 + 2 * tcount] = clock64();
+                if (dbg && warp == 2 && lane == 0 && tcount - (uint32_t)a.dbg_skip < 4u) dbg[44 + 2 * (tcount - a.dbg_skip)] = clock64();
 #pragma unroll 1
                 for (int blk = ehalf; blk < NBLK; blk += 4) {
                     if (blk + 2 < NBLK) prefetch(blk + 2, rb1);
@@ -421,7 +567,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
-                                float val = __uint_as_float(r[j]) + bias_s[py * NH + c0 + j];
+                                float val = __uint_as_float(r[j]);  // bias: already in the accumulator
                                 if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
                                 v[c0 + j] = val;
                             }
@@ -453,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (dbg && warp == 2 && lane == 0 && tcount < 4) dbg[45 + 2 * tcount] = clock64();
+            if (dbg && warp == 2 && lane == 0 && tcount - (uint32_t)a.dbg_skip < 4u) dbg[45 + 2 * (tcount - a.dbg_skip)] = clock64();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
@@ -490,7 +636,8 @@ static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st)
     constexpr int W_BYTES = TAPS * 2 * N * 16;
     const int nplanes = a.split_in ? 2 : 1;
     const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
-    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256 + 2 * N * sizeof(float);
+    // barriers etc. (256) + slope_s + ones tile (4 KB) + bias B matrix + identity matrix (res_mode 3)
+    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256 + N * sizeof(float) + 2 * 128 * 16 + (size_t)2 * N * 16 + (a.res_mode == 3 ? (size_t)2 * (2 * N - 16) * 16 : 0);
     if (smem > 227 * 1024) return -2;
     // the attribute is per device: one process may drive several GPUs (src/main.cpp -g 0,1,...)
     static size_t configured[64] = {};
@@ -530,6 +677,12 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     const int cgroups = (a.s2 ? 4 : 1) * (a.Cin / 8);
     if (a.out_s2d && ((a.H | a.W) & 1)) return -7;
     if (a.batch < 1) a.batch = 1;
+    if (a.res_mode == 3) return -9;  // internal value, selected below
+    // residual == the conv's own input (the ResConv blocks): let the tensor core add it (identity tap, see the kernel)
+    static const bool ident_ok = !(getenv("RIFE_B200_RES_IDENT") && atoi(getenv("RIFE_B200_RES_IDENT")) == 0);
+    if (ident_ok && a.res_mode == 1 && a.epi == TC_EPI_C8 && !a.s2 && a.res == (const __half*)in && a.Cin == a.N && a.Cout == a.N && a.N <= 128 && (!a.res_split) == (!a.split_in) &&
+        (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
+        a.res_mode = 3;
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
     cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};

@@ -23,7 +23,7 @@ struct TcConvArgs {
     int H, W, Cin, Cout, N; // N = GEMM columns (Cout for conv, 4*ocs for deconv)
     int split_in, split_out, res_split;
     int epi;                // TC_EPI_*
-    int res_mode;           // 0 none, 1 add before activation, 2 add after activation
+    int res_mode;           // 0 none, 1 add before activation, 2 add after activation (3 is internal: the launcher turns 1 into 3 when res == in)
     int act_mode;           // 0 none, 1 leaky(slope), 2 prelu, 3 sigmoid (deconv epilogue only)
     int ocs, ps;            // deconv: output-channel slots per parity, PixelShuffle factor (1 = none)
     int out_planes;         // deconv + PixelShuffle: store only the first out_planes planes (0 = all)
@@ -33,6 +33,8 @@ struct TcConvArgs {
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
+    int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
+    int dbg_flags;                  // timing experiments only (results wrong): 8 = empty epilogue
 };
 
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.

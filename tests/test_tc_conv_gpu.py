@@ -35,6 +35,19 @@ def test_conv3x3_res_leaky(pkg, c, split):
     assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
 
 
+@pytest.mark.parametrize("c", [32, 48, 64, 96, 128, 192])
+@pytest.mark.parametrize("split", [1, 0])
+def test_conv3x3_self_residual(pkg, c, split):
+    """Residual == the conv's own input (the ResConv blocks): the kernel adds it on the tensor core through an identity
+    tap instead of reading it in the epilogue; passing res=x selects that path."""
+    h, w = 21, 70
+    x, wgt, b, _ = _data(c, c, h, w, 9, seed=100 + c)
+    x = np.ascontiguousarray(x, np.float32)
+    o_tc, o_ref = pkg.selftest_conv(0, x, wgt, b, res=x, slope=0.2, split=bool(split))
+    mx, tol, bad = _check(o_tc, o_ref, split)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
 def test_conv3x3_single_taps(pkg):
     """One non-zero tap at a time: localises a wrong shared-memory view (row/column shift) to its (dy,dx)."""
     c, h, w = 64, 10, 64
