@@ -184,7 +184,7 @@ int Engine::set_option(const std::string& key, int value) {
     }
     if (key == "fast") { use_fast_ = value; return 0; }
     if (key == "plain_blocks") {  // bit mask of IFBlocks whose residual chain uses plain fp16 activations (fused path)
-        plain_mask_ = value & 15;
+        plain_mask_ = value & 255;  // bits 4-7 (experimental): block k's head tensor / conv0 input in plain fp16
         for (Lane* L : lanes_) if (L->fast) L->fast->set_plain_mask(plain_mask_);
         return 0;
     }

@@ -5,6 +5,9 @@
 //   head<S> U = bilinear(d_{k-1}, S'); F = F + S'*U[0:4] (k = 1: F = S'*U[0:4]); M = M + U[4]   (the update after block k-1)
 //           x = cat(bilinear(cat(warp(I0,F01), warp(I1,F23), T, M), 1/S), bilinear(F, 1/S) / S)   (S = 4, 2, 1)
 //   tail    F3 = F + d3[0:4]; M3 = M + d3[4]; out = warp(I0,F3_01)*sigmoid(M3) + warp(I1,F3_23)*(1 - sigmoid(M3)) -> u8
+// The kernels read the frames as padded RGBX bytes (one launch converts every distinct frame of a batch) and evaluate
+// v = u8 * (1/255) on the fly -- exactly what rife_preproc would have stored (src/rife.cpp:4152-4211) -- so the fp32 planar
+// copies of the frames (25 MB each at 1080p, gathered 4 x per pair) never exist on this path.
 // Arithmetic is the generic executor's, operation for operation (same lin_coeff, H pass then V pass, same warp), so the
 // two paths agree to fp32 rounding; Engine::load() additionally checks the fast path against the generic executor on a
 // small random frame pair and silently keeps the generic path when the graph is not the expected one.
@@ -12,7 +15,12 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "fused_v46.h"
 #include "kernels.h"
@@ -23,8 +31,9 @@ namespace rife {
 namespace {
 
 // interp.cpp:54-91 (coefficient in double, rounded to float)
-__device__ __forceinline__ void lin_coeff(int d, int in_n, int out_n, int& s, float& f) {
-    double scale = (double)in_n / out_n;
+// `scale` = in_n / out_n, which on this path is always an exact power of two (8, 4, 2, 1/2, 1/4, 1/8) known at compile
+// time, so the reference's double division is folded; the rest of the arithmetic is unchanged
+__device__ __forceinline__ void lin_coeff(int d, double scale, int in_n, int& s, float& f) {
     float fx = (float)((d + 0.5) * scale - 0.5);
     int sx = (int)floorf(fx);
     fx -= sx;
@@ -40,9 +49,33 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ p, int w, int 
     float row1 = r1[0] * a0 + r1[1] * a1;
     return row0 * b0 + row1 * b1;
 }
+// One frame, padded to wp x hp and widened to 4 bytes per pixel (R, G, B, 0; zeros in the pad region) by rgbx_kernel:
+// a tap is one aligned 32-bit load.  The padded planar float image the reference works on (rife_preproc: v * 1/255)
+// is evaluated on the fly.
+struct Frame {
+    const uchar4* p;
+    int wp;
+};
+__device__ __forceinline__ void px3(const Frame& f, int x, int y, float* o) {
+    const uchar4 q = __ldg(f.p + (size_t)y * f.wp + x);
+    o[0] = (float)q.x * (1 / 255.f);
+    o[1] = (float)q.y * (1 / 255.f);
+    o[2] = (float)q.z * (1 / 255.f);
+}
+// bilinear tap of the three colour planes (interp.cpp:92-175: horizontal pass, then vertical)
+__device__ __forceinline__ void bilerp3(const Frame& f, int sy, int sx, float a0, float a1, float b0, float b1, float* o) {
+    float p00[3], p01[3], p10[3], p11[3];
+    px3(f, sx, sy, p00); px3(f, sx + 1, sy, p01); px3(f, sx, sy + 1, p10); px3(f, sx + 1, sy + 1, p11);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float row0 = p00[c] * a0 + p01[c] * a1;
+        float row1 = p10[c] * a0 + p11[c] * a1;
+        o[c] = row0 * b0 + row1 * b1;
+    }
+}
 // src/warp.cpp:96-168 for one pixel: taps and weights (alpha / beta taken after clamping)
 struct WarpTap {
-    int i00, i01, i10, i11;
+    int x0, x1, y0, y1;
     float a, b;
 };
 __device__ __forceinline__ WarpTap warp_tap(int x, int y, float fx, float fy, int w, int h) {
@@ -56,13 +89,18 @@ __device__ __forceinline__ WarpTap warp_tap(int x, int y, float fx, float fy, in
     WarpTap t;
     t.a = sx - x0;
     t.b = sy - y0;
-    t.i00 = y0 * w + x0; t.i01 = y0 * w + x1; t.i10 = y1 * w + x0; t.i11 = y1 * w + x1;
+    t.x0 = x0; t.x1 = x1; t.y0 = y0; t.y1 = y1;
     return t;
 }
-__device__ __forceinline__ float warp_sample(const float* __restrict__ p, const WarpTap& t) {
-    float v4 = p[t.i00] * (1 - t.a) + p[t.i01] * t.a;
-    float v5 = p[t.i10] * (1 - t.a) + p[t.i11] * t.a;
-    return v4 * (1 - t.b) + v5 * t.b;
+__device__ __forceinline__ void warp_sample3(const Frame& f, const WarpTap& t, float* o) {
+    float p00[3], p01[3], p10[3], p11[3];
+    px3(f, t.x0, t.y0, p00); px3(f, t.x1, t.y0, p01); px3(f, t.x0, t.y1, p10); px3(f, t.x1, t.y1, p11);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float v4 = p00[c] * (1 - t.a) + p01[c] * t.a;
+        float v5 = p10[c] * (1 - t.a) + p11[c] * t.a;
+        o[c] = v4 * (1 - t.b) + v5 * t.b;
+    }
 }
 __device__ __forceinline__ uint32_t pack2h(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
 
@@ -88,33 +126,48 @@ __device__ __forceinline__ void store_c8_s2d_16(__half* out, const float* v, int
 }
 
 // x0 = Interp(cat(I0, I1, T), 1/8): flownet.param:9-10
+// Per-image kernel arguments are passed as __grid_constant__ structs: indexing them with blockIdx.z then reads the
+// constant bank directly (a plain by-value struct is first copied to local memory, ~20 stores per thread).
 struct TBatch {
     float t[V46_MAX_BATCH];
 };
 struct OutBatch {
     uint8_t* p[V46_MAX_BATCH];
 };
+struct InBatch {
+    const uchar4* p0[V46_MAX_BATCH];
+    const uchar4* p1[V46_MAX_BATCH];
+};
+struct SrcBatch {
+    const uint8_t* p[2 * V46_MAX_BATCH];
+};
+// rife_preproc without the float conversion: RGB u8 HWC (w x h) -> RGBX [hp][wp], zeros outside the image
+__global__ void rgbx_kernel(const __grid_constant__ SrcBatch sb, int w, int h, int wp, int hp, uchar4* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wp) return;
+    uchar4 q = make_uchar4(0, 0, 0, 0);
+    if (x < w && y < h) {
+        const uint8_t* p = sb.p[blockIdx.z] + ((size_t)y * w + x) * 3;
+        q = make_uchar4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0);
+    }
+    out[((size_t)blockIdx.z * hp + y) * wp + x] = q;
+}
 
-__global__ void head0_kernel(const float* __restrict__ I0, const float* __restrict__ I1, TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+__global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
     const int b = blockIdx.z;
     const float t = tb.t[b];
-    I0 += (size_t)b * 3 * hp * wp;
-    I1 += (size_t)b * 3 * hp * wp;
+    const Frame I0 = {ib.p0[b], wp}, I1 = {ib.p1[b], wp};
     out += (size_t)b * 16 * oh * ow * 2;
     int sx, sy;
     float fx, fy;
-    lin_coeff(ox, wp, ow, sx, fx);
-    lin_coeff(oy, hp, oh, sy, fy);
+    lin_coeff(ox, 8.0, wp, sx, fx);
+    lin_coeff(oy, 8.0, hp, sy, fy);
     const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const size_t plane = (size_t)hp * wp;
     float v[16];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        v[c] = bilerp(I0 + c * plane, wp, sy, sx, a0, a1, b0, b1);
-        v[3 + c] = bilerp(I1 + c * plane, wp, sy, sx, a0, a1, b0, b1);
-    }
+    bilerp3(I0, sy, sx, a0, a1, b0, b1, v);
+    bilerp3(I1, sy, sx, a0, a1, b0, b1, v + 3);
     v[6] = (t * a0 + t * a1) * b0 + (t * a0 + t * a1) * b1;  // the timestep plane goes through the same resize arithmetic
 #pragma unroll
     for (int c = 7; c < 16; c++) v[c] = 0.f;
@@ -129,15 +182,14 @@ __global__ void head0_kernel(const float* __restrict__ I0, const float* __restri
 // footprint and keeps the 2x2 (S > 1) or 1 (S = 1) tap pixels the down-sampling reads -- for these integer scales the
 // taps always lie inside the thread's own footprint, so no other thread's update is needed.
 template <int S, int SP, bool FIRST>
-__global__ void head_update_kernel(const float* __restrict__ I0, const float* __restrict__ I1, float* __restrict__ F, float* __restrict__ M,
-                                   const float* __restrict__ d, int dh, int dw, TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+__global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __restrict__ F, float* __restrict__ M, const float* __restrict__ d, int dh, int dw,
+                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
     const size_t plane = (size_t)hp * wp, dplane = (size_t)dh * dw;
     const int b = blockIdx.z;
     const float t = tb.t[b];
-    I0 += (size_t)b * 3 * plane;
-    I1 += (size_t)b * 3 * plane;
+    const Frame I0 = {ib.p0[b], wp}, I1 = {ib.p1[b], wp};
     F += (size_t)b * 4 * plane;
     M += (size_t)b * plane;
     d += (size_t)b * 6 * dplane;
@@ -151,7 +203,7 @@ __global__ void head_update_kernel(const float* __restrict__ I0, const float* __
 #pragma unroll
     for (int fx = 0; fx < S; fx++) {
         float f;
-        lin_coeff(S * ox + fx, dw, wp, usx[fx], f);
+        lin_coeff(S * ox + fx, 1.0 / SP, dw, usx[fx], f);
         ua0[fx] = 1.f - f;
         ua1[fx] = f;
     }
@@ -160,7 +212,7 @@ __global__ void head_update_kernel(const float* __restrict__ I0, const float* __
         const int y = S * oy + fy;
         int usy;
         float f;
-        lin_coeff(y, dh, hp, usy, f);
+        lin_coeff(y, 1.0 / SP, dh, usy, f);
         const float ub0 = 1.f - f, ub1 = f;
         float nf[4][S], nm[S];
         const size_t p0 = (size_t)y * wp + S * ox;  // first footprint pixel of this row: S consecutive floats per plane
@@ -209,11 +261,8 @@ __global__ void head_update_kernel(const float* __restrict__ I0, const float* __
         const float f0 = tapF[ty][tx][0], f1 = tapF[ty][tx][1], f2 = tapF[ty][tx][2], f3 = tapF[ty][tx][3];
         WarpTap t0 = warp_tap(x, y, f0, f1, wp, hp);
         WarpTap t1 = warp_tap(x, y, f2, f3, wp, hp);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            e[c] = warp_sample(I0 + c * plane, t0);
-            e[3 + c] = warp_sample(I1 + c * plane, t1);
-        }
+        warp_sample3(I0, t0, e);
+        warp_sample3(I1, t1, e + 3);
         e[6] = t;
         e[7] = tapM[ty][tx];
         e[8] = f0; e[9] = f1; e[10] = f2; e[11] = f3;
@@ -228,8 +277,8 @@ __global__ void head_update_kernel(const float* __restrict__ I0, const float* __
     } else {
         int sx, sy;
         float fx, fy;
-        lin_coeff(ox, wp, ow, sx, fx);  // == S*ox + T0 for these scales; kept for the exact coefficient arithmetic
-        lin_coeff(oy, hp, oh, sy, fy);
+        lin_coeff(ox, (double)S, wp, sx, fx);  // == S*ox + T0 for these scales; kept for the exact coefficient arithmetic
+        lin_coeff(oy, (double)S, hp, sy, fy);
         const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
         float e00[12], e01[12], e10[12], e11[12];
         at(0, 0, e00);
@@ -251,19 +300,21 @@ __global__ void head_update_kernel(const float* __restrict__ I0, const float* __
 }
 
 // last update + blend + rife_postproc: flownet.param:202-217, src/rife.cpp:4375-4398, mat_pixel.cpp:158
-__global__ void tail_kernel(const float* __restrict__ I0, const float* __restrict__ I1, const float* __restrict__ F, const float* __restrict__ M,
-                            const float* __restrict__ d3, int hp, int wp, OutBatch ob, int w, int h) {
+__global__ void tail_kernel(const __grid_constant__ InBatch ib, const float* __restrict__ F, const float* __restrict__ M, const float* __restrict__ d3, int hp, int wp,
+                            const __grid_constant__ OutBatch ob,
+                            int w, int h) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
+    const int b = blockIdx.z;
     {
         const size_t pl = (size_t)hp * wp;
-        const int b = blockIdx.z;
-        I0 += (size_t)b * 3 * pl; I1 += (size_t)b * 3 * pl; F += (size_t)b * 4 * pl; M += (size_t)b * pl; d3 += (size_t)b * 6 * pl;
+        F += (size_t)b * 4 * pl; M += (size_t)b * pl; d3 += (size_t)b * 6 * pl;
     }
-    uint8_t* __restrict__ rgb = ob.p[blockIdx.z];
+    const Frame I0 = {ib.p0[b], wp}, I1 = {ib.p1[b], wp};
+    uint8_t* __restrict__ rgb = ob.p[b];
     // the reference CPU path reads the first w*h floats of each padded output channel contiguously (rife.cpp:4375-4387)
-    const size_t idx = (size_t)y * w + x;
-    const int Y = (int)(idx / wp), X = (int)(idx - (size_t)Y * wp);
+    const uint32_t idx = (uint32_t)y * (uint32_t)w + (uint32_t)x;  // < 2^31: w * h pixels of one frame
+    const int Y = w == wp ? y : (int)(idx / (uint32_t)wp), X = w == wp ? x : (int)(idx - (uint32_t)Y * (uint32_t)wp);
     const size_t plane = (size_t)hp * wp, pi = (size_t)Y * wp + X;
     const float f0 = F[pi] + d3[pi], f1 = F[plane + pi] + d3[plane + pi];
     const float f2 = F[2 * plane + pi] + d3[2 * plane + pi], f3 = F[3 * plane + pi] + d3[3 * plane + pi];
@@ -274,11 +325,14 @@ __global__ void tail_kernel(const float* __restrict__ I0, const float* __restric
     const float om = 1.f - m;     // BinaryOp rsub
     WarpTap t0 = warp_tap(X, Y, f0, f1, wp, hp);
     WarpTap t1 = warp_tap(X, Y, f2, f3, wp, hp);
-    uint8_t* o = rgb + idx * 3;
+    float s0[3], s1[3];
+    warp_sample3(I0, t0, s0);
+    warp_sample3(I1, t1, s1);
+    uint8_t* o = rgb + (size_t)idx * 3;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        float w0 = warp_sample(I0 + c * plane, t0) * m;
-        float w1 = warp_sample(I1 + c * plane, t1) * om;
+        float w0 = s0[c] * m;
+        float w1 = s1[c] * om;
         float v = (w0 + w1) * 255.f + 0.5f;
         int iv = (int)v;
         o[c] = (uint8_t)min(max(iv, 0), 255);
@@ -286,6 +340,46 @@ __global__ void tail_kernel(const float* __restrict__ I0, const float* __restric
 }
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// RIFE_B200_KTIME=1: CUDA-event time of every stage of run_batch (diagnostics; synchronises after each batch)
+struct StageTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    std::vector<std::pair<std::string, double>> acc;
+    std::vector<int> cnt;
+    int batches = 0;
+    StageTimer() { const char* e = getenv("RIFE_B200_KTIME"); on = e && atoi(e) != 0; }
+    void begin(cudaStream_t st) { if (!on) return; names.clear(); mark(nullptr, st); }
+    void mark(const char* name, cudaStream_t st) {
+        if (!on) return;
+        size_t i = names.size();
+        if (ev.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        cudaEventRecord(ev[i], st);
+        names.push_back(name ? name : "");
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        for (size_t i = 1; i < names.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            size_t j = 0;
+            for (; j < acc.size(); j++) if (acc[j].first == names[i]) break;
+            if (j == acc.size()) { acc.push_back({names[i], 0.0}); cnt.push_back(0); }
+            acc[j].second += ms; cnt[j]++;
+        }
+        batches++;
+    }
+    ~StageTimer() {
+        if (!on || !batches) return;
+        double tot = 0;
+        for (auto& a : acc) tot += a.second;
+        fprintf(stderr, "[rife_b200 ktime] %d batches, %.3f ms per batch\n", batches, tot / batches);
+        for (size_t j = 0; j < acc.size(); j++)
+            fprintf(stderr, "[rife_b200 ktime] %-22s %8.1f us/batch (%2d launches) %5.1f %%\n", acc[j].first.c_str(), 1e3 * acc[j].second / batches, cnt[j] / batches, 100 * acc[j].second / tot);
+    }
+};
 
 }  // namespace
 
@@ -338,12 +432,11 @@ int V46Runner::ensure(int w, int h, int batch, std::string& err) {
         return p;
     };
     const size_t plane = (size_t)wp * hp;
-    I0_ = (float*)alloc(B * 3 * plane * 4);
-    I1_ = (float*)alloc(B * 3 * plane * 4);
+    rgbx_ = (uchar4*)alloc(2 * B * plane * 4);
     F_ = (float*)alloc(B * 4 * plane * 4);
     M_ = (float*)alloc(B * plane * 4);
     static const int S[4] = {8, 4, 2, 1};
-    bool fail = !I0_ || !I1_ || !F_ || !M_;
+    bool fail = !F_ || !M_ || !rgbx_;
     for (int k = 0; k < 4; k++) {
         const size_t hk = hp / S[k], wk = wp / S[k];
         const int c = 192 >> 0;
@@ -415,39 +508,63 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
     static const int S[4] = {8, 4, 2, 1};
     TBatch tb;
     OutBatch ob;
-    for (int b = 0; b < V46_MAX_BATCH; b++) { tb.t[b] = b < n ? ts[b] : 0.f; ob.p[b] = b < n ? d_out[b] : nullptr; }
-    for (int b = 0; b < n; b++) {
-        launch_preproc(d_in0[b], w, h, I0_ + (size_t)b * 3 * plane, wp, hp, 0, st);
-        launch_preproc(d_in1[b], w, h, I1_ + (size_t)b * 3 * plane, wp, hp, 0, st);
+    InBatch ib;
+    SrcBatch sb;
+    int nu = 0;  // distinct frames of this batch: the second frame of pair i is usually the first frame of pair i + 1
+    auto slot = [&](const uint8_t* p) {
+        for (int i = 0; i < nu; i++) if (sb.p[i] == p) return i;
+        sb.p[nu] = p;
+        return nu++;
+    };
+    for (int b = 0; b < V46_MAX_BATCH; b++) {
+        tb.t[b] = b < n ? ts[b] : 0.f;
+        ob.p[b] = b < n ? d_out[b] : nullptr;
+        ib.p0[b] = b < n ? rgbx_ + (size_t)slot(d_in0[b]) * plane : nullptr;
+        ib.p1[b] = b < n ? rgbx_ + (size_t)slot(d_in1[b]) * plane : nullptr;
     }
+    for (int i = nu; i < 2 * V46_MAX_BATCH; i++) sb.p[i] = nullptr;
+    static thread_local StageTimer tm;
+    tm.begin(st);
+    rgbx_kernel<<<dim3(cdiv(wp, 128), hp, nu), 128, 0, st>>>(sb, w, h, wp, hp, rgbx_);
+    g_launch_count++;
+    tm.mark("rgbx", st);
+    char nm[32];
     for (int k = 0; k < 4; k++) {
         const int hk = hp / S[k], wk = wp / S[k];
         dim3 g(cdiv(wk, 128), hk, n);
         // head of block k, fused with the flow / mask update that follows block k-1
-        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(I0_, I1_, tb, hp, wp, hk, wk, x_[0]);
-        else if (k == 1) head_update_kernel<4, 8, true><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[1]);
-        else if (k == 2) head_update_kernel<2, 4, false><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[1], hp / 4, wp / 4, tb, hp, wp, hk, wk, x_[2]);
-        else head_update_kernel<1, 2, false><<<g, 128, 0, st>>>(I0_, I1_, F_, M_, d_[2], hp / 2, wp / 2, tb, hp, wp, hk, wk, x_[3]);
+        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(ib, tb, hp, wp, hk, wk, x_[0]);
+        else if (k == 1) head_update_kernel<4, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[1]);
+        else if (k == 2) head_update_kernel<2, 4, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, tb, hp, wp, hk, wk, x_[2]);
+        else head_update_kernel<1, 2, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
+        snprintf(nm, sizeof nm, "b%d head", k); tm.mark(nm, st);
         const int* L = &conv_[k * 11];
         // precision: the block-head tensor and the two stride-2 convs that follow it always run on split (fp32-equivalent)
         // operands -- measured: making conv0's output / conv1's input plain fp16 doubles the 1-LSB flips and, with all four
         // blocks plain, produces 4-LSB errors on the README frames; the residual chain and the deconv of a block are split
         // unless the block is listed in plain_mask_ (plain fp16 activations there)
         const bool sp = !((plain_mask_ >> k) & 1);
-        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, true, true, st);   // 3x3 s2, leaky
+        const bool hsp = !((plain_mask_ >> (4 + k)) & 1);  // experimental: read only the hi plane of the head tensor
+        int r = conv(L[0], x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, hsp, true, st);    // 3x3 s2, leaky
+        snprintf(nm, sizeof nm, "b%d conv0", k); tm.mark(nm, st);
         r |= conv(L[1], y0_[k], a_[k], nullptr, nullptr, hk / 4, wk / 4, false, n, true, sp, st);       // 3x3 s2, leaky
+        snprintf(nm, sizeof nm, "b%d conv1", k); tm.mark(nm, st);
         __half* cur = a_[k];
         __half* nxt = b_[k];
         for (int j = 0; j < 8; j++) {                                                                 // y = leaky(conv(y) + y)
             r |= conv(L[2 + j], cur, nxt, cur, nullptr, hk / 4, wk / 4, false, n, sp, sp, st);
             __half* tmp = cur; cur = nxt; nxt = tmp;
         }
+        snprintf(nm, sizeof nm, "b%d res x8", k); tm.mark(nm, st);
         r |= conv(L[10], cur, nullptr, nullptr, d_[k], hk / 4, wk / 4, false, n, sp, false, st);        // deconv + PixelShuffle -> flow<k>
+        snprintf(nm, sizeof nm, "b%d deconv", k); tm.mark(nm, st);
         if (r) { err = "tensor-core conv launch failed in block " + std::to_string(k); return -3; }
     }
-    tail_kernel<<<dim3(cdiv(w, 128), h, n), 128, 0, st>>>(I0_, I1_, F_, M_, d_[3], hp, wp, ob, w, h);
+    tail_kernel<<<dim3(cdiv(w, 128), h, n), 128, 0, st>>>(ib, F_, M_, d_[3], hp, wp, ob, w, h);
     g_launch_count++;
+    tm.mark("tail", st);
+    tm.end(st);
     return 0;
 }
 

@@ -22,7 +22,7 @@ public:
     bool ok() const { return ok_; }
     // bit k set: the residual chain of IFBlock k runs on plain fp16 activations (half the tensor work, ~2^-11 operand
     // rounding); 0 = every tensor-core activation is split hi+lo
-    void set_plain_mask(int m) { plain_mask_ = m & 15; }
+    void set_plain_mask(int m) { plain_mask_ = m & 255; }
     int run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err);
     int run_batch(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st,
                   std::string& err);
@@ -39,7 +39,8 @@ private:
     std::vector<int> conv_;  // the 44 conv / deconv layer indices in graph order
     int wp_ = 0, hp_ = 0, cap_ = 0;
     std::vector<void*> bufs_;
-    float *I0_ = nullptr, *I1_ = nullptr, *F_ = nullptr, *M_ = nullptr, *d_[4] = {};
+    uchar4* rgbx_ = nullptr;  // the distinct frames of a batch, padded RGBX
+    float *F_ = nullptr, *M_ = nullptr, *d_[4] = {};
     __half *x_[4] = {}, *y0_[4] = {}, *a_[4] = {}, *b_[4] = {};
 };
 

@@ -28,7 +28,7 @@ r = pkg.RIFE(0, False, False, False, 1, False, True)
 r.load(parity.model_dir("rife-v4.6"))
 for name, (a, b) in cases:
     ref, _ = parity.run_oracle("rife-v4.6", a, b, 0.5, threads=16)
-    for mask in (0, 8, 12, 14, 15):
+    for mask in [int(m, 0) for m in os.environ.get("RIFE_STUDY_MASKS", "0,8,12,14,15").split(",")]:
         r.set_option("plain_blocks", mask)
         out = r.process(a, b, 0.5)
         res = parity.compare(out, ref)

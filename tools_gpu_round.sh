@@ -1,4 +1,4 @@
-mkdir -p gpurun_out/s6
-RIFE_BENCH_PAIRS=8 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/s6/launches.csv python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline > gpurun_out/s6/b.log 2>&1
-tail -2 gpurun_out/s6/b.log | cut -c1-300
-wc -l gpurun_out/s6/launches.csv
+mkdir -p gpurun_out/s10
+timeout 900 python -m pytest tests/test_parity_gpu.py -q -x > gpurun_out/s10/parity.log 2>&1; tail -4 gpurun_out/s10/parity.log
+RIFE_B200_KTIME=1 timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 --lanes 1 > gpurun_out/s10/bench_l1.json 2> gpurun_out/s10/ktime.txt; grep ktime gpurun_out/s10/ktime.txt
+timeout 300 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/s10/bench.json 2> gpurun_out/s10/bench.err; cat gpurun_out/s10/bench.json | cut -c1-200; grep -o '"e2e": {[^}]*}' gpurun_out/s10/bench.json; grep -o '"clocks": {[^}]*}' gpurun_out/s10/bench.json
