@@ -192,6 +192,8 @@ def selftest_conv(mode, x, weight, bias, res=None, slope=0.2, split=True, ps=2, 
     bias = np.ascontiguousarray(bias, np.float32)
     cin, h, w = x.shape
     cout = weight.shape[0]
+    if mode == 3:
+        assert ps == 2 and cout == 24
     if mode == 0:
         oshape = (cout, h, w)
     elif mode == 2:

@@ -210,6 +210,9 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     GUARD_BEGIN
     using namespace rife;
     if (!in || !weight || !bias || !out_tc || !out_ref || cin <= 0 || cout <= 0 || h <= 0 || w <= 0) return RIFE_B200_ERR_ARG;
+    // mode 3 = mode 1 restricted to the first five PixelShuffle planes (the IFNet flow head: the launcher's out_planes = 5)
+    const bool planes5 = mode == 3;
+    if (planes5) { if (ps != 2 || cout != 24) return RIFE_B200_ERR_ARG; mode = 1; }
     if (mode != 2 && cin % 16) return RIFE_B200_ERR_ARG;
     if (mode == 2) return selftest_conv_s2(gpuid, cin, cout, h, w, split, in, weight, bias, slope, out_tc, out_ref);
     if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
@@ -263,6 +266,7 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     a.res_mode = res ? 1 : 0;
     a.act_mode = mode == 0 ? 1 : 0;
     a.ocs = ocs; a.ps = ps;
+    a.out_planes = planes5 ? 5 : 0;
     int r = launch_tc_conv(a, d_in8, st);
     if (r) { fprintf(stderr, "launch_tc_conv failed: %d\n", r); return RIFE_B200_ERR_INTERNAL; }
     if (mode == 0) launch_c8_to_planar(d_out8, d_out_tc, cout, h, w, split, st);

@@ -140,6 +140,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait::ld variants that name the destination registers as in/out operands: values read after the wait formally depend
 // on it, so the compiler cannot schedule a consumer of an in-flight tcgen05.ld above the wait (software-pipelined loads)
@@ -550,6 +553,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 if constexpr (N <= 96) {
                 const int r_ = a.ps;
                 const int OH = a.H * 2 * r_, OW = a.W * 2 * r_;
+                if (N == 96 && r_ == 2 && a.act_mode != 3 && a.out_planes == 5) {
+                    // the IFNet flow head (24 channels -> PixelShuffle(2) -> 4 flow + 1 mask planes, the sixth plane is never
+                    // read): per (accumulator m, output-row parity py) 2 x 20 of the 48 columns are needed; they go out
+                    // as 10 coalesced 16-byte stores straight from the loaded registers.  The bias is already in the accumulator.
+                    constexpr int OCS = 24, NH = 48, NIT = 2 * MT;
+                    auto ld = [&](int it, uint32_t* r) {
+                        const uint32_t t = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (it >> 1) * N + (it & 1) * NH;
+                        tmem_ld16(t, r); tmem_ld4(t + 16, r + 16);                  // px = 0: oc 0..19
+                        tmem_ld16(t + OCS, r + 20); tmem_ld4(t + OCS + 16, r + 36);  // px = 1: oc 0..19
+                    };
+                    auto wt = [&](uint32_t* r) { tmem_ld_wait_dep32(r); tmem_ld_wait_dep16(r + 24); };  // one wait; 40 of the registers named
+                    auto stv = [&](int it, const uint32_t* r) {
+                        const int m = it >> 1, py = it & 1;
+                        const int y = y0 + 2 * m + yrow;
+                        if (!(xvalid && y < a.H)) return;
+                        float* o = outf_b + (size_t)((2 * y + py) * 2) * OW + 4 * x;
+#pragma unroll
+                        for (int qq = 0; qq < 5; qq++)
+#pragma unroll
+                            for (int sh = 0; sh < 2; sh++) {
+                                const int o0 = qq * 4 + sh * 2;
+                                *reinterpret_cast<float4*>(o + ((size_t)qq * OH + sh) * OW) =
+                                    make_float4(__uint_as_float(r[o0]), __uint_as_float(r[o0 + 1]), __uint_as_float(r[20 + o0]), __uint_as_float(r[20 + o0 + 1]));
+                            }
+                    };
+                    uint32_t ra[40];
+#pragma unroll 1
+                    for (int it = ehalf; it < NIT; it += 2) {
+                        ld(it, ra);
+                        wt(ra);
+                        stv(it, ra);
+                    }
+                } else
 #pragma unroll 1
                 for (int m = ehalf; m < MT; m += 2) {
                     const int y = y0 + 2 * m + yrow;

@@ -48,6 +48,18 @@ def test_conv3x3_self_residual(pkg, c, split):
     assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
 
 
+@pytest.mark.parametrize("cin", [64, 96, 128, 192])
+@pytest.mark.parametrize("split", [1, 0])
+def test_flow_head_deconv_five_planes(pkg, cin, split):
+    """deconv4x4s2 (24 channels) + PixelShuffle(2) keeping the five planes the flow / mask update reads."""
+    h, w = 9, 70
+    x, wgt, b, _ = _data(cin, 24, h, w, 16, seed=cin + 5)
+    o_tc, o_ref = pkg.selftest_conv(3, x, wgt, b, split=bool(split), ps=2)
+    mx, tol, bad = _check(o_tc[:5], o_ref[:5], split)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+    assert not o_tc[5].any()
+
+
 def test_conv3x3_single_taps(pkg):
     """One non-zero tap at a time: localises a wrong shared-memory view (row/column shift) to its (dy,dx)."""
     c, h, w = 64, 10, 64
