@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {"1080p": (1920, 1080, "rife-v4.6 1920x1080 synthetic frame-pair stream (BASELINE configs[1])"),
              "4k": (3840, 2160, "rife-v4.6 3840x2160 UHD-flag stream (BASELINE configs[2]; -u is a no-op for v4 nets)")}
 GFLOP_PER_FRAME = {"1080p": 175.2, "4k": 701.0}
-PAIRS_PER_STEP = int(os.environ.get("RIFE_BENCH_PAIRS", "64"))  # profiling runs shrink the step
+PAIRS_PER_STEP = int(os.environ.get("RIFE_BENCH_PAIRS", "0"))  # 0 = default for the workload (128 pairs of 1080p, 32 of 4K); profiling runs shrink the step
 DISTINCT_FRAMES = 9  # consecutive frames of the synthetic stream; pairs cycle through them
 MODEL = "rife-v4.6"
 
@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--timestep", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global PAIRS_PER_STEP
+    if PAIRS_PER_STEP <= 0:
+        PAIRS_PER_STEP = 32 if args.workload == "4k" else 128
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

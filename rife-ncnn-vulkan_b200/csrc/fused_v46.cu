@@ -196,9 +196,15 @@ __global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_co
 // One thread owns one output pixel and its S x S full-resolution footprint: it updates (and stores) F, M for the whole
 // footprint and keeps the 2x2 (S > 1) or 1 (S = 1) tap pixels the down-sampling reads -- for these integer scales the
 // taps always lie inside the thread's own footprint, so no other thread's update is needed.
-template <int S, int SP, bool FIRST>
+// MODE 0 (k = 1): F = SP*U, M = U[4]; nothing is stored and only the tap pixels are evaluated -- the next head
+//                 recomputes these values from the small d_0 instead of reading 5 full-resolution planes back.
+// MODE 1 (k = 2): the old F, M are recomputed as SPP*bilinear(dprev, SPP) (same operations as MODE 0), updated, stored.
+// MODE 2 (k = 3): the old F, M are read from memory, updated, stored (the tail reads them).
+template <int S, int SP, int MODE, int SPP>
 __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __restrict__ F, float* __restrict__ M, const float* __restrict__ d, int dh, int dw,
-                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+                                   const float* __restrict__ dprev, int pdh, int pdw, const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow,
+                                   __half* __restrict__ out) {
+    constexpr bool FIRST = MODE == 0;
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
     const size_t plane = (size_t)hp * wp, dplane = (size_t)dh * dw;
@@ -208,6 +214,8 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
     F += (size_t)b * 4 * plane;
     M += (size_t)b * plane;
     d += (size_t)b * 6 * dplane;
+    const size_t pdplane = (size_t)pdh * pdw;
+    if (MODE == 1) dprev += (size_t)b * 6 * pdplane;
     out += (size_t)b * 16 * oh * ow * 2;
     constexpr int T0 = S == 1 ? 0 : S / 2 - 1;  // first tap inside the footprint (S = 4: 1, S = 2: 0)
     constexpr int NT = S == 1 ? 1 : 2;
@@ -222,8 +230,20 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
         ua0[fx] = 1.f - f;
         ua1[fx] = f;
     }
+    int psx[S];
+    float pa0[S], pa1[S];
+    if (MODE == 1) {
+#pragma unroll
+        for (int fx = 0; fx < S; fx++) {
+            float f;
+            lin_coeff(S * ox + fx, 1.0 / SPP, pdw, psx[fx], f);
+            pa0[fx] = 1.f - f;
+            pa1[fx] = f;
+        }
+    }
 #pragma unroll
     for (int fy = 0; fy < S; fy++) {
+        if (MODE == 0 && !(fy >= T0 && fy < T0 + NT)) continue;  // nothing stored: only the tap rows matter
         const int y = S * oy + fy;
         int usy;
         float f;
@@ -243,13 +263,25 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
             else base[p0] = src[0];
         };
         float oldf[4][S], oldm[S];
-        if (!FIRST) {
+        if (MODE == 2) {
 #pragma unroll
             for (int c = 0; c < 4; c++) load_row(F + c * plane, oldf[c]);
             load_row(M, oldm);
+        } else if (MODE == 1) {
+            int psy;
+            float pf;
+            lin_coeff(y, 1.0 / SPP, pdh, psy, pf);
+            const float pb0 = 1.f - pf, pb1 = pf;
+#pragma unroll
+            for (int fx = 0; fx < S; fx++) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) oldf[c][fx] = bilerp(dprev + c * pdplane, pdw, psy, psx[fx], pa0[fx], pa1[fx], pb0, pb1) * (float)SPP;
+                oldm[fx] = bilerp(dprev + 4 * pdplane, pdw, psy, psx[fx], pa0[fx], pa1[fx], pb0, pb1);
+            }
         }
 #pragma unroll
         for (int fx = 0; fx < S; fx++) {
+            if (MODE == 0 && !(fx >= T0 && fx < T0 + NT)) continue;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const float u = bilerp(d + c * dplane, dw, usy, usx[fx], ua0[fx], ua1[fx], ub0, ub1);
@@ -258,9 +290,11 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
             const float um = bilerp(d + 4 * dplane, dw, usy, usx[fx], ua0[fx], ua1[fx], ub0, ub1);
             nm[fx] = FIRST ? um : oldm[fx] + um;
         }
+        if (MODE != 0) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) store_row(F + c * plane, nf[c]);
-        store_row(M, nm);
+            for (int c = 0; c < 4; c++) store_row(F + c * plane, nf[c]);
+            store_row(M, nm);
+        }
 #pragma unroll
         for (int fx = 0; fx < S; fx++) {
             if (fy >= T0 && fy < T0 + NT && fx >= T0 && fx < T0 + NT) {
@@ -552,9 +586,9 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         dim3 g(cdiv(wk, 128), hk, n);
         // head of block k, fused with the flow / mask update that follows block k-1
         if (k == 0) head0_kernel<<<g, 128, 0, st>>>(ib, tb, hp, wp, hk, wk, x_[0]);
-        else if (k == 1) head_update_kernel<4, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[1]);
-        else if (k == 2) head_update_kernel<2, 4, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, tb, hp, wp, hk, wk, x_[2]);
-        else head_update_kernel<1, 2, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, tb, hp, wp, hk, wk, x_[3]);
+        else if (k == 1) head_update_kernel<4, 8, 0, 8><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 8, wp / 8, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[1]);
+        else if (k == 2) head_update_kernel<2, 4, 1, 8><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[2]);
+        else head_update_kernel<1, 2, 2, 8><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3]);
         g_launch_count++;
         snprintf(nm, sizeof nm, "b%d head", k); tm.mark(nm, st);
         const int* L = &conv_[k * 11];

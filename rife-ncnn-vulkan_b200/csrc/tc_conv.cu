@@ -173,7 +173,7 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) { return (uint32_t
 }  // namespace
 
 // N = UMMA N (output columns per accumulator), MT = accumulators (128 flattened positions each) per tile,
-// STAGES = pipeline depth.
+// STAGES = minimum pipeline depth; the launcher raises it (TcConvArgs::stages, up to 8) to what shared memory allows.
 // TAPS = 9: stride-1 conv (every K chunk uses the 9 shifted views).  TAPS = 4: stride-2 conv over a space-to-depth
 // input (4 parity sub-images [py][px] of H/2 x W/2, each a run of K chunks): input row 2y+dy-1 is row y-1 of the odd
 // sub-image for dy = 0, row y of the even one for dy = 1 and row y of the odd one for dy = 2 (columns alike), so a
@@ -189,13 +189,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nplanes = a.split_in ? 2 : 1;
-    const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes + 1024);  // +1024: overrun pad for the last tap of the last slab
-    uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;
+    // a.wres: the packed weights of the whole layer stay in shared memory for the life of the (persistent) CTA and a
+    // pipeline stage carries activations only; otherwise every stage re-streams its 16-channel weight slice from L2
+    // (per tile that is more bytes than the activations themselves).
+    const int stage_bytes = ((A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)) + 1023) & ~1023;
+    const int NST = a.stages;  // pipeline depth (<= 8), chosen by the launcher
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_bytes + 1024);  // +1024: overrun pad for the last tap of the last slab
+    uint64_t* empty = full + 8;
+    uint64_t* acc_full = empty + 8;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* slope_s = reinterpret_cast<float*>(tmem_slot + 4);  // per-channel (slope - 1), PReLU epilogue only
+    uint64_t* wbar = acc_empty + 2;
+    uint64_t* scratch_bar = wbar + 1;  // diagnostics only (dbg_flags 64)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch_bar + 1);
+    float* slope_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);  // per-channel (slope - 1), PReLU epilogue only; 16-byte aligned
     // Constant MMA operands, built once per CTA:
     //  ones  : A tile 128 x 16 with K columns 0..2 = 1      }  first MMA of every tile: D = ones * biasB = the fp32 bias
     //  biasB : B tile 16 x N, K rows 0..2 = bias as hi+lo+lo2 }  (three fp16 pieces), so no epilogue touches the bias
@@ -204,9 +210,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     //          N-16+k has its one in K column k); the B view of K chunk kc starts (N-16-16*kc) rows in, which puts the
     //          ones at columns n = 16*kc + k.  The centre view of the halo tile is the A operand: no global residual read.
     constexpr int IROWS = 2 * N - 16;
-    __half* ones = reinterpret_cast<__half*>(smem + (size_t)STAGES * stage_bytes + 1024 + 256 + N * sizeof(float));
+    __half* ones = reinterpret_cast<__half*>(smem + (size_t)NST * stage_bytes + 1024 + 256 + N * sizeof(float));
     __half* biasB = ones + 2 * 128 * 8;
     __half* ident = biasB + 2 * N * 8;
+    uint8_t* wres = smem + (((size_t)NST * stage_bytes + 1024 + 256 + N * sizeof(float) + 2 * 128 * 16 + 2 * N * 16 + 2 * IROWS * 16 + 127) & ~(size_t)127);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_img = a.tiles_x * a.tiles_y;
@@ -216,8 +223,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     const uint32_t dskip = (uint32_t)(a.dbg_skip * KC);  // diagnostics: first recorded pipeline iteration
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        mbar_init(wbar, 1);
+        mbar_init(scratch_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     }
@@ -265,20 +274,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            if (a.wres) {
+                mbar_arrive_expect_tx(wbar, (uint32_t)(KC * W_BYTES));
+                for (int kc = 0; kc < KC; kc++) bulk_load_1d(wres + (size_t)kc * W_BYTES, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, wbar);
+            }
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
                 const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
                 const int x0 = tx * TVALID, y0 = ty * (2 * MT);
                 for (int kc = 0; kc < KC; kc++, it++) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + W_BYTES));
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)));
                     for (int p = 0; p < nplanes; p++)
                         tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc, bimg);
-                    bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
+                    if (!a.wres) bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                     if (dbg && it - dskip < 12u) dbg[1 + it - dskip] = clock64();
+                    if (++s == NST) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -290,7 +304,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             constexpr uint32_t A_LBO = ((uint32_t)(ROWS * TWP * 16) >> 4) << 16;
             constexpr uint32_t B_LBO = ((uint32_t)(N * 16) >> 4) << 16;
+            // (The weight-stationary form tcgen05.mma.ws -- the MT MMAs of a tap sharing one B fetch -- was measured and is
+            // not used: same tile period as this plain form, see profiles/r1_epilogue/mma_ws_ab.txt.)
             uint32_t it = 0, tcount = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            if (a.wres) {
+                mbar_wait(wbar, 0);
+                tc_fence_after();
+            }
+            const uint32_t wres_addr = smem_u32(wres);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
                 const int buf = tcount & 1;
                 const uint32_t aph = (tcount >> 1) & 1;
@@ -304,14 +327,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     for (int m = 0; m < MT; m++) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);
                 }
                 for (int kc = 0; kc < KC; kc++, it++) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     if (dbg && it - dskip < 12u && lane == 0) dbg[16 + it - dskip] = clock64();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_base = (st >> 4) | A_LBO;
-                    const uint32_t b_base = ((st + nplanes * A_PLANE) >> 4) | B_LBO;
+                    const uint32_t b_base = ((a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE) >> 4) | B_LBO;
                     constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
                     if constexpr (TAPS == 9) {
 #pragma unroll
@@ -345,8 +366,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                             }
                     }
+                    if (a.dbg_flags & 64) umma_commit_elect(scratch_bar);  // timing experiment: what does one more commit per stage cost?
                     umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
                     if (dbg && it - dskip < 12u && lane == 0) dbg[32 + it - dskip] = clock64();
+                    if (++s == NST) { s = 0; ph ^= 1; }
                 }
                 umma_commit_elect(&acc_full[buf]);
             }
@@ -666,14 +689,32 @@ static EncodeTiledFn get_encode() {
 }
 
 template <int N, int MT, int STAGES, int TAPS>
-static int launch_t(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t st) {
+    TcConvArgs a = a_in;
     constexpr int ROWS = 2 * MT + 2;
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;
     constexpr int W_BYTES = TAPS * 2 * N * 16;
     const int nplanes = a.split_in ? 2 : 1;
-    const int stage_bytes = ((A_PLANE * nplanes + W_BYTES) + 1023) & ~1023;
-    // barriers etc. (256) + slope_s + ones tile (4 KB) + bias B matrix + identity matrix (res_mode 3)
-    const size_t smem = (size_t)STAGES * stage_bytes + 1024 + 256 + N * sizeof(float) + 2 * 128 * 16 + (size_t)2 * N * 16 + (a.res_mode == 3 ? (size_t)2 * (2 * N - 16) * 16 : 0);
+    // barriers etc. (256) + slope_s + ones tile (4 KB) + bias B matrix + identity matrix (res_mode 3, or resident weights)
+    const size_t consts = 1024 + 256 + N * sizeof(float) + 2 * 128 * 16 + (size_t)2 * N * 16;
+    const size_t ident_bytes = (size_t)2 * (2 * N - 16) * 16;
+    // resident weights (stride-1 kernels): the whole packed layer next to activation-only stages, when it fits
+    static const bool wres_ok = !(getenv("RIFE_B200_WRES") && atoi(getenv("RIFE_B200_WRES")) == 0);
+    const size_t w_all = (size_t)(a.Cin / 16) * W_BYTES;
+    const size_t budget = 227 * 1024;
+    const size_t stage_a = (size_t)((A_PLANE * nplanes + 1023) & ~1023), stage_aw = (size_t)((A_PLANE * nplanes + W_BYTES + 1023) & ~1023);
+    // resident weights need at least STAGES activation-only stages next to the whole layer
+    a.wres = wres_ok && TAPS == 9 && ((STAGES * stage_a + consts + ident_bytes + 127) & ~(size_t)127) + w_all <= budget;
+    const int stage_bytes = (int)(a.wres ? stage_a : stage_aw);
+    const size_t fixed = a.wres ? consts + ident_bytes + 127 + w_all : consts + (a.res_mode == 3 ? ident_bytes : 0);
+    // pipeline depth: what shared memory allows (the stages are what hides the L2 / HBM latency of the activation tiles)
+    static const int max_stages = getenv("RIFE_B200_STAGES") ? atoi(getenv("RIFE_B200_STAGES")) : 8;
+    int nst = (int)((budget - fixed) / stage_bytes);
+    if (nst > max_stages) nst = max_stages;
+    if (nst > 8) nst = 8;
+    if (nst < STAGES) nst = STAGES;
+    a.stages = nst;
+    const size_t smem = a.wres ? (((size_t)nst * stage_bytes + consts + ident_bytes + 127) & ~(size_t)127) + w_all : (size_t)nst * stage_bytes + fixed;
     if (smem > 227 * 1024) return -2;
     // the attribute is per device: one process may drive several GPUs (src/main.cpp -g 0,1,...)
     static size_t configured[64] = {};

@@ -32,9 +32,11 @@ struct TcConvArgs {
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
+    int stages;                     // filled by the launcher: pipeline depth (<= 8)
+    int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
     int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
-    int dbg_flags;                  // timing experiments only (results wrong): 8 = empty epilogue
+    int dbg_flags;                  // timing experiments only: 8 = empty epilogue (results wrong), 64 = one extra tcgen05.commit per stage
 };
 
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
