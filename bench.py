@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--plain-blocks", type=int, default=-1, help="bit mask of IFBlocks whose residual chain uses plain fp16 activations (-1 = library default)")
+    ap.add_argument("--recompute-fm", type=int, default=-1, help="fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2; -1 = library default)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per lock-step batch on the fused path (0 = auto from the frame size)")
     ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
     ap.add_argument("--tta", action="store_true")
@@ -220,6 +221,8 @@ def main():
     eng.set_option("batch", args.batch)
     if args.plain_blocks >= 0:
         eng.set_option("plain_blocks", args.plain_blocks)
+    if args.recompute_fm >= 0:
+        eng.set_option("recompute_fm", args.recompute_fm)
 
     # synthetic frames: a short stream, distinct per rank; PAIRS_PER_STEP consecutive pairs per step
     nframes = min(PAIRS_PER_STEP, DISTINCT_FRAMES - 1) + 1
@@ -339,7 +342,7 @@ def main():
                          if args.precision == 1 else ("f32" if args.precision == 0 else "f16 / f32 accumulate"),
                 "data": "synthetic",
                 "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
-                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch, "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "fused_v46_path": bool(eng.get_option("fast_active")),
+                           "tta_temporal": args.tta_temporal, "pairs_per_step": PAIRS_PER_STEP, "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch, "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "recompute_fm": eng.get_option("recompute_fm"), "fused_v46_path": bool(eng.get_option("fast_active")),
                            "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic"},
                 "gflop_per_frame": GFLOP_PER_FRAME[args.workload] if args.model == MODEL and not (args.tta or args.tta_temporal) else None,
                 "model_tflops": value * GFLOP_PER_FRAME[args.workload] / 1000.0 if args.model == MODEL and not (args.tta or args.tta_temporal) else None,

@@ -188,6 +188,11 @@ int Engine::set_option(const std::string& key, int value) {
         for (Lane* L : lanes_) if (L->fast) L->fast->set_plain_mask(plain_mask_);
         return 0;
     }
+    if (key == "recompute_fm") {  // fused path: 0 store the full-resolution flow / mask planes, 1 / 2 rebuild them from the block outputs (fused_v46.h)
+        recompute_fm_ = value < 0 ? 0 : (value > 2 ? 2 : value);
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_recompute(recompute_fm_);
+        return 0;
+    }
     if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
     if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
@@ -202,6 +207,7 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "fast") *value = use_fast_;
     else if (key == "batch") *value = batch_;
     else if (key == "plain_blocks") *value = plain_mask_;
+    else if (key == "recompute_fm") *value = recompute_fm_;
     else if (key == "fast_active") *value = fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1;
     else { last_error = "unknown option " + key; return -1; }
     return 0;
@@ -217,6 +223,7 @@ void Engine::setup_fast() {
     std::string err;
     for (Lane* L : lanes_) {
         L->fast = new V46Runner();
+        L->fast->set_recompute(recompute_fm_);
         if (L->fast->init(&nets_[0], lanes_[0]->run[0], err)) {
             for (Lane* L2 : lanes_) { delete L2->fast; L2->fast = nullptr; }
             return;

@@ -23,6 +23,9 @@ public:
     // bit k set: the residual chain of IFBlock k runs on plain fp16 activations (half the tensor work, ~2^-11 operand
     // rounding); 0 = every tensor-core activation is split hi+lo
     void set_plain_mask(int m) { plain_mask_ = m & 255; }
+    // 0: flow / mask planes stored at full resolution between the block-2 head and the tail; 1: block-3 head stops
+    // storing them; 2: never stored, rebuilt from the per-block flow tensors where needed (same arithmetic, fewer HBM bytes)
+    void set_recompute(int m) { recompute_ = m < 0 ? 0 : (m > 2 ? 2 : m); }
     int run(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st, std::string& err);
     int run_batch(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st,
                   std::string& err);
@@ -36,6 +39,7 @@ private:
     bool ok_ = false;
     float slope_ = 0.2f;
     int plain_mask_ = 0;
+    int recompute_ = 0;
     std::vector<int> conv_;  // the 44 conv / deconv layer indices in graph order
     int wp_ = 0, hp_ = 0, cap_ = 0;
     std::vector<void*> bufs_;

@@ -1,0 +1,317 @@
+// emu_fused.cpp -- TEST INFRASTRUCTURE.  Compiles the device code of the fused rife-v4.6 path
+// (rife-ncnn-vulkan_b200/csrc/fused_v46_kernels.cuh) for the HOST: a launch becomes a loop over the grid, blockIdx /
+// threadIdx are thread-local globals.  No GPU, no CUDA runtime.  It checks what can be checked without the conv stacks:
+//   * the three storage variants of the full-resolution flow / mask planes (recompute_fm 0 / 1 / 2) feed the block heads
+//     and the tail the same values: head tensors x2, x3 and the output frame must be bit-identical;
+//   * the head / tail kernels against a direct restatement of SURVEY.md Appendix B written with whole-image loops
+//     (upsample -> axpy -> warp -> downsample), i.e. the fusion (footprints, tap bookkeeping) changes nothing.
+// Build: g++ -O1 -ffp-contract=off -I/usr/local/cuda/include -I<csrc> emu_fused.cpp   (tests/test_emu_cpu.py)
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include <cuda_fp16.h>
+#include <vector_functions.h>
+#include <vector_types.h>
+
+// ---- the bits of the CUDA programming model the kernels use ----
+static thread_local uint3 blockIdx, threadIdx;
+static thread_local dim3 blockDim, gridDim;
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+
+#define RIFE_FUSED_EMU 1
+#include "fused_v46_kernels.cuh"
+
+using namespace rife::fusedk;
+using rife::V46_MAX_BATCH;
+
+template <class K, class... A>
+static void launch(dim3 g, dim3 b, K k, A... a) {
+    gridDim = g;
+    blockDim = b;
+    for (unsigned z = 0; z < g.z; z++)
+        for (unsigned y = 0; y < g.y; y++)
+            for (unsigned x = 0; x < g.x; x++)
+                for (unsigned t = 0; t < b.x; t++) {
+                    blockIdx = make_uint3(x, y, z);
+                    threadIdx = make_uint3(t, 0, 0);
+                    k(a...);
+                }
+}
+static unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static uint32_t rng_state = 12345u;
+static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+static float frand(float lo, float hi) { return lo + (hi - lo) * (float)(rnd() & 0xffff) / 65535.f; }
+
+// ---- whole-image restatement of the dataflow between the conv stacks ----
+// ncnn Interp bilinear (interp.cpp:54-175): coefficients in double -> float, horizontal pass then vertical
+static void ref_lin(int d, double scale, int in_n, int& s, float& f) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= in_n - 1) { sx = in_n - 2; fx = 1.f; }
+    s = sx; f = fx;
+}
+static void ref_resize(const float* in, int ih, int iw, float* out, int oh, int ow) {
+    if (ih == oh && iw == ow) { memcpy(out, in, sizeof(float) * ih * iw); return; }
+    const double sy_ = (double)ih / oh, sx_ = (double)iw / ow;
+    for (int y = 0; y < oh; y++) {
+        int sy; float fy;
+        ref_lin(y, sy_, ih, sy, fy);
+        for (int x = 0; x < ow; x++) {
+            int sx; float fx;
+            ref_lin(x, sx_, iw, sx, fx);
+            const float* r0 = in + (size_t)sy * iw + sx;
+            const float* r1 = r0 + iw;
+            float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+            float row0 = r0[0] * a0 + r0[1] * a1;
+            float row1 = r1[0] * a0 + r1[1] * a1;
+            out[(size_t)y * ow + x] = row0 * b0 + row1 * b1;
+        }
+    }
+}
+// src/warp.cpp:96-168 on one plane
+static void ref_warp(const float* img, const float* fx, const float* fy, int h, int w, float* out) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float sx = x + fx[(size_t)y * w + x], sy = y + fy[(size_t)y * w + x];
+            int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+            int x1 = x0 + 1, y1 = y0 + 1;
+            x0 = std::min(std::max(x0, 0), w - 1); y0 = std::min(std::max(y0, 0), h - 1);
+            x1 = std::min(std::max(x1, 0), w - 1); y1 = std::min(std::max(y1, 0), h - 1);
+            float a = sx - x0, b = sy - y0;
+            float v4 = img[(size_t)y0 * w + x0] * (1 - a) + img[(size_t)y0 * w + x1] * a;
+            float v5 = img[(size_t)y1 * w + x0] * (1 - a) + img[(size_t)y1 * w + x1] * a;
+            out[(size_t)y * w + x] = v4 * (1 - b) + v5 * b;
+        }
+}
+
+struct Case {
+    int w, h, wp, hp, n;
+    std::vector<uchar4> rgbx;            // 2 * n frames, padded
+    std::vector<float> d[4];             // per block: n x 6 planes at 1/8, 1/4, 1/2, 1/1
+    TBatch tb;
+    InBatch ib;
+};
+
+static void make_case(Case& c, int w, int h, int n) {
+    c.w = w; c.h = h; c.n = n;
+    c.wp = (w + 31) / 32 * 32; c.hp = (h + 31) / 32 * 32;
+    const size_t plane = (size_t)c.wp * c.hp;
+    c.rgbx.assign(2 * n * plane, make_uchar4(0, 0, 0, 0));
+    for (int f = 0; f < 2 * n; f++)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int base = (int)(120 + 60 * sinf(0.13f * (x + 2 * f)) * cosf(0.09f * (y - f)));
+                c.rgbx[f * plane + (size_t)y * c.wp + x] = make_uchar4((unsigned char)std::min(255, base + (int)(rnd() & 31)), (unsigned char)std::min(255, base + (int)(rnd() & 15)),
+                                                                        (unsigned char)std::max(0, base - (int)(rnd() & 31)), 0);
+            }
+    static const int S[4] = {8, 4, 2, 1};
+    for (int k = 0; k < 4; k++) {
+        const size_t hk = c.hp / S[k], wk = c.wp / S[k];
+        c.d[k].resize((size_t)n * 6 * hk * wk);
+        // flow increments of a few pixels at this block's own scale, mask increments of order 1
+        for (size_t i = 0; i < c.d[k].size(); i++) {
+            const int ch = (int)((i / (hk * wk)) % 6);
+            c.d[k][i] = ch < 4 ? frand(-1.5f, 1.5f) : frand(-2.f, 2.f);
+        }
+    }
+    for (int b = 0; b < V46_MAX_BATCH; b++) {
+        c.tb.t[b] = b < n ? 0.125f + 0.1f * b : 0.f;
+        c.ib.p0[b] = b < n ? c.rgbx.data() + (size_t)(2 * b) * plane : nullptr;
+        c.ib.p1[b] = b < n ? c.rgbx.data() + (size_t)(2 * b + 1) * plane : nullptr;
+    }
+}
+
+struct Result {
+    std::vector<__half> x[4];
+    std::vector<uint8_t> out;
+};
+
+// the launches of V46Runner::run_batch that are not convolutions, with `rc` = the recompute_fm option
+static void run_fused(Case& c, int rc, Result& r) {
+    const int wp = c.wp, hp = c.hp, n = c.n;
+    const size_t plane = (size_t)wp * hp;
+    std::vector<float> F((size_t)n * 4 * plane, 1e30f), M((size_t)n * plane, 1e30f);  // poison: reading an unwritten plane shows
+    static const int S[4] = {8, 4, 2, 1};
+    for (int k = 0; k < 4; k++) r.x[k].assign((size_t)n * 16 * (hp / S[k]) * (wp / S[k]) * 2, __float2half_rn(-77.f));
+    const bool rc2 = rc >= 2, rc1 = rc == 1;
+    for (int k = 0; k < 4; k++) {
+        const int hk = hp / S[k], wk = wp / S[k];
+        dim3 g(cdiv(wk, 128), hk, n), b(128, 1, 1);
+        float* d0 = c.d[0].data(); float* d1 = c.d[1].data(); float* d2 = c.d[2].data();
+        __half* x = r.x[k].data();
+        if (k == 0) launch(g, b, head0_kernel, c.ib, c.tb, hp, wp, hk, wk, x);
+        else if (k == 1) launch(g, b, head_update_kernel<4, 8, 0, 8, false>, c.ib, F.data(), M.data(), (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+        else if (k == 2) {
+            if (rc2) launch(g, b, head_update_kernel<2, 4, 1, 8, false>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+            else launch(g, b, head_update_kernel<2, 4, 1, 8, true>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+        } else {
+            if (rc2) launch(g, b, head_update_kernel<1, 2, 3, 4, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, c.tb, hp, wp, hk, wk, x);
+            else if (rc1) launch(g, b, head_update_kernel<1, 2, 2, 8, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+            else launch(g, b, head_update_kernel<1, 2, 2, 8, true>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+        }
+    }
+    r.out.assign((size_t)n * c.w * c.h * 3, 0);
+    OutBatch ob;
+    for (int b = 0; b < V46_MAX_BATCH; b++) ob.p[b] = b < n ? r.out.data() + (size_t)b * c.w * c.h * 3 : nullptr;
+    DSrc ds;
+    ds.d[0] = c.d[0].data(); ds.d[1] = c.d[1].data(); ds.d[2] = c.d[2].data();
+    dim3 tg(cdiv(c.w, 128), c.h, n), tbk(128, 1, 1);
+    if (rc2) launch(tg, tbk, tail_kernel<2>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
+    else if (rc1) launch(tg, tbk, tail_kernel<1>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
+    else launch(tg, tbk, tail_kernel<0>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
+}
+
+// value of channel ch of head tensor k (C8 space-to-depth, hi + lo planes) at output pixel (oy, ox)
+static float head_at(const Result& r, int k, int b, int oh, int ow, int ch, int oy, int ox) {
+    const __half* base = r.x[k].data() + (size_t)b * 16 * oh * ow * 2;
+    const size_t sub = (size_t)(oh >> 1) * (ow >> 1), pl = (size_t)16 * oh * ow;
+    const int par = (oy & 1) * 2 + (ox & 1), g = ch >> 3, j = ch & 7;
+    const size_t off = (((size_t)par * 2 + g) * sub + (size_t)(oy >> 1) * (ow >> 1) + (ox >> 1)) * 8 + j;
+    return __half2float(base[off]) + __half2float(base[pl + off]);
+}
+
+// whole-image reference of one pair: returns the head tensors (12 or 7 channels, fp32) and the output frame
+static void run_reference(const Case& c, int b, std::vector<float> xr[4], std::vector<uint8_t>& out) {
+    const int wp = c.wp, hp = c.hp;
+    const size_t plane = (size_t)wp * hp;
+    std::vector<float> I[2][3];
+    for (int f = 0; f < 2; f++)
+        for (int ch = 0; ch < 3; ch++) {
+            I[f][ch].resize(plane);
+            const uchar4* p = f == 0 ? c.ib.p0[b] : c.ib.p1[b];
+            for (size_t i = 0; i < plane; i++) {
+                const uchar4 q = p[i];
+                I[f][ch][i] = (float)(ch == 0 ? q.x : (ch == 1 ? q.y : q.z)) * (1 / 255.f);
+            }
+        }
+    std::vector<float> T(plane, c.tb.t[b]);
+    static const int S[4] = {8, 4, 2, 1};
+    std::vector<float> F[4], M(plane, 0.f);
+    for (auto& f : F) f.assign(plane, 0.f);
+    std::vector<float> tmp(plane), W[2][3];
+    for (int k = 0; k < 4; k++) {
+        const int hk = hp / S[k], wk = wp / S[k];
+        const size_t pk = (size_t)hk * wk;
+        if (k == 0) {
+            xr[0].assign(7 * pk, 0.f);
+            for (int ch = 0; ch < 3; ch++) ref_resize(I[0][ch].data(), hp, wp, &xr[0][ch * pk], hk, wk);
+            for (int ch = 0; ch < 3; ch++) ref_resize(I[1][ch].data(), hp, wp, &xr[0][(3 + ch) * pk], hk, wk);
+            ref_resize(T.data(), hp, wp, &xr[0][6 * pk], hk, wk);
+        } else {
+            // update after block k-1
+            const int sp = S[k - 1], dh = hp / sp, dw = wp / sp;
+            const float* d = c.d[k - 1].data() + (size_t)b * 6 * dh * dw;
+            for (int ch = 0; ch < 5; ch++) {
+                ref_resize(d + (size_t)ch * dh * dw, dh, dw, tmp.data(), hp, wp);
+                for (size_t i = 0; i < plane; i++) {
+                    if (ch < 4) F[ch][i] = k == 1 ? tmp[i] * (float)sp : F[ch][i] * 1.f + tmp[i] * (float)sp;
+                    else M[i] = k == 1 ? tmp[i] : M[i] + tmp[i];
+                }
+            }
+            for (int f = 0; f < 2; f++)
+                for (int ch = 0; ch < 3; ch++) {
+                    W[f][ch].resize(plane);
+                    ref_warp(I[f][ch].data(), F[2 * f].data(), F[2 * f + 1].data(), hp, wp, W[f][ch].data());
+                }
+            xr[k].assign(12 * pk, 0.f);
+            for (int f = 0; f < 2; f++)
+                for (int ch = 0; ch < 3; ch++) ref_resize(W[f][ch].data(), hp, wp, &xr[k][(3 * f + ch) * pk], hk, wk);
+            ref_resize(T.data(), hp, wp, &xr[k][6 * pk], hk, wk);
+            ref_resize(M.data(), hp, wp, &xr[k][7 * pk], hk, wk);
+            for (int ch = 0; ch < 4; ch++) {
+                ref_resize(F[ch].data(), hp, wp, &xr[k][(8 + ch) * pk], hk, wk);
+                if (S[k] > 1) for (size_t i = 0; i < pk; i++) xr[k][(8 + ch) * pk + i] = xr[k][(8 + ch) * pk + i] / (float)S[k];
+            }
+        }
+    }
+    // final update + blend + quantise (flownet.param:202-217, rife.cpp:4375-4398)
+    const float* d3 = c.d[3].data() + (size_t)b * 6 * plane;
+    for (int ch = 0; ch < 4; ch++) for (size_t i = 0; i < plane; i++) F[ch][i] = F[ch][i] + d3[ch * plane + i];
+    for (size_t i = 0; i < plane; i++) M[i] = M[i] + d3[4 * plane + i];
+    std::vector<float> O[3];
+    for (int ch = 0; ch < 3; ch++) {
+        std::vector<float> w0(plane), w1(plane);
+        ref_warp(I[0][ch].data(), F[0].data(), F[1].data(), hp, wp, w0.data());
+        ref_warp(I[1][ch].data(), F[2].data(), F[3].data(), hp, wp, w1.data());
+        O[ch].resize(plane);
+        for (size_t i = 0; i < plane; i++) {
+            float m = M[i];
+            m = fminf(m, 88.3762626647949f); m = fmaxf(m, -88.3762626647949f);
+            m = 1.f / (1.f + expf(-m));
+            O[ch][i] = w0[i] * m + w1[i] * (1.f - m);
+        }
+    }
+    out.resize((size_t)c.w * c.h * 3);
+    for (size_t i = 0; i < (size_t)c.w * c.h; i++)  // contiguous read of the padded planes (rife.cpp:4375-4387)
+        for (int ch = 0; ch < 3; ch++) {
+            int iv = (int)(O[ch][i] * 255.f + 0.5f);
+            out[i * 3 + ch] = (uint8_t)std::min(std::max(iv, 0), 255);
+        }
+}
+
+int main(int argc, char** argv) {
+    int fails = 0;
+    const int sizes[][3] = {{64, 64, 2}, {100, 70, 3}, {160, 96, 1}, {96, 128, 2}};
+    for (auto& sz : sizes) {
+        Case c;
+        make_case(c, sz[0], sz[1], sz[2]);
+        Result r0, r1, r2;
+        run_fused(c, 0, r0);
+        run_fused(c, 1, r1);
+        run_fused(c, 2, r2);
+        static const int S[4] = {8, 4, 2, 1};
+        for (int k = 0; k < 4; k++) {
+            const size_t nb = r0.x[k].size() * sizeof(__half);
+            if (memcmp(r0.x[k].data(), r1.x[k].data(), nb)) { printf("FAIL %dx%d: head %d differs, recompute 1\n", sz[0], sz[1], k); fails++; }
+            if (memcmp(r0.x[k].data(), r2.x[k].data(), nb)) { printf("FAIL %dx%d: head %d differs, recompute 2\n", sz[0], sz[1], k); fails++; }
+        }
+        if (r0.out != r1.out) { printf("FAIL %dx%d: output differs, recompute 1\n", sz[0], sz[1]); fails++; }
+        if (r0.out != r2.out) { printf("FAIL %dx%d: output differs, recompute 2\n", sz[0], sz[1]); fails++; }
+        // against the whole-image restatement
+        double worst = 0;
+        size_t odiff = 0, omax = 0;
+        for (int b = 0; b < c.n; b++) {
+            std::vector<float> xr[4];
+            std::vector<uint8_t> oref;
+            run_reference(c, b, xr, oref);
+            for (int k = 0; k < 4; k++) {
+                const int hk = c.hp / S[k], wk = c.wp / S[k], nch = k == 0 ? 7 : 12;
+                for (int ch = 0; ch < 16; ch++)
+                    for (int y = 0; y < hk; y++)
+                        for (int x = 0; x < wk; x++) {
+                            const float got = head_at(r0, k, b, hk, wk, ch, y, x);
+                            const float want = ch < nch ? xr[k][((size_t)ch * hk + y) * wk + x] : 0.f;
+                            // hi + lo fp16 carries ~22 bits: compare with a relative 2^-20 / absolute 1e-6 allowance
+                            const double e = fabs((double)got - want) / std::max(1.0, fabs((double)want));
+                            if (e > worst) worst = e;
+                        }
+            }
+            const uint8_t* o = r0.out.data() + (size_t)b * c.w * c.h * 3;
+            for (size_t i = 0; i < oref.size(); i++) {
+                size_t dd = (size_t)abs((int)o[i] - (int)oref[i]);
+                odiff += dd != 0;
+                omax = std::max(omax, dd);
+            }
+        }
+        printf("%dx%d n=%d: head tensors vs restatement max rel err %.3g, output bytes differing %zu (max %zu)\n", sz[0], sz[1], sz[2], worst, odiff, omax);
+        if (worst > 2e-6) { printf("FAIL %dx%d: head tensor mismatch\n", sz[0], sz[1]); fails++; }
+        if (omax > 0) { printf("FAIL %dx%d: output mismatch\n", sz[0], sz[1]); fails++; }
+    }
+    printf(fails ? "EMU FAILED (%d)\n" : "EMU OK\n", fails);
+    return fails ? 1 : 0;
+}

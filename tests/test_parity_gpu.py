@@ -213,3 +213,34 @@ def test_batched_lockstep_equals_single_pair_path(pkg):
     r.close()
     for s_, o in zip(singles, outs):
         assert np.array_equal(s_, o)
+
+
+@pytest.mark.parametrize("w,h", [(256, 160), (100, 70), (1920, 1080)])
+def test_v46_recompute_fm_modes_are_bit_identical(pkg, w, h):
+    """recompute_fm 1 / 2: the full-resolution flow / mask planes are rebuilt from the per-block flow tensors instead of
+    being stored and re-read (fused_v46.cu).  Same operations in the same order, so the frames must be identical -- for a
+    single pair, for a lock-step batch with different timesteps, and for a ragged size (w % 32 != 0: the tail's
+    contiguous-read quirk of src/rife.cpp:4375-4387)."""
+    _need("rife-v4.6")
+    nb = 3 if w * h > 1000000 else 8
+    frames = [parity.synth.frame(k, w, h, dx=5, dy=3) for k in range(nb + 1)]
+    ts = [0.25 + 0.0625 * i for i in range(nb)]
+    v2, v4 = pkg.family_flags("rife-v4.6")
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir("rife-v4.6"))
+    assert r.get_option("fast_active") == 1
+    r.set_option("lanes", 1)
+    r.set_option("batch", nb)
+    results = {}
+    for mode in (0, 1, 2):
+        r.set_option("recompute_fm", mode)
+        assert r.get_option("recompute_fm") == mode
+        single = r.process(frames[0], frames[1], 0.5)
+        outs = [np.empty_like(frames[0]) for _ in range(nb)]
+        r.process_batch_ptr([f.ctypes.data for f in frames[:nb]], [f.ctypes.data for f in frames[1:]], w, h, ts, [o.ctypes.data for o in outs])
+        results[mode] = [single] + outs
+    r.close()
+    assert results[0][0].std() > 5
+    for mode in (1, 2):
+        for a_, b_ in zip(results[0], results[mode]):
+            assert np.array_equal(a_, b_), (mode, parity.compare(a_, b_))
