@@ -110,6 +110,13 @@ int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w
                             const float* weight, const float* bias, const float* res, float slope, float* out_tc,
                             float* out_ref);
 
+/* Diagnostics (host only, no GPU): the weight packing of the tcgen05 kernel, fp16 bit patterns.
+ * mode 0: conv3x3 w[cout][cin][3][3]; mode 1: deconv4x4 s2 w[cout][cin][4][4] with `ocs` column slots per output parity.
+ * out_elems must be (cin/16)*9*2*N*8.  paired: 0 = [kc][tap][half][N][8]; 1 = [kc][dx][half][3N: dy2|dy0|dy1][8]
+ * (the layout of the paired MMA issue, 2N <= 256); -1 = whatever this process uses (environment RIFE_B200_PAIR). */
+int rife_b200_debug_pack_weights(int mode, int cout, int cin, int N, int ocs, int paired, const float* w,
+                                 unsigned short* out, size_t out_elems);
+
 /* kernels launched by this library since process start (bench.py reports it as gpu_launches) */
 unsigned long long rife_b200_launch_count(void);
 

@@ -310,6 +310,21 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     GUARD_END
 }
 
+// diagnostics (host only, no GPU needed): the tensor-core weight packing, so a CPU test can replay the MMA operand views
+extern "C" int rife_b200_debug_pack_weights(int mode, int cout, int cin, int N, int ocs, int paired, const float* w, unsigned short* out, size_t out_elems) {
+    GUARD_BEGIN
+    using namespace rife;
+    if (!w || !out || cin % 16 || N % 16 || cout <= 0 || cout > N) return RIFE_B200_ERR_ARG;
+    std::vector<uint16_t> pk;
+    if (mode == 0) pack_conv3x3_weights(w, cout, cin, N, pk, paired);
+    else if (mode == 1) { if (4 * ocs > N || cout > ocs) return RIFE_B200_ERR_ARG; pack_deconv4x4_weights(w, cout, cin, ocs, N, pk, paired); }
+    else return RIFE_B200_ERR_ARG;
+    if (pk.size() != out_elems) return RIFE_B200_ERR_ARG;
+    memcpy(out, pk.data(), pk.size() * sizeof(uint16_t));
+    return 0;
+    GUARD_END
+}
+
 extern "C" int rife_b200_bench_conv(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int iters);
 extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int cin, int cout, int h, int w, int split, int batch, int iters);
 

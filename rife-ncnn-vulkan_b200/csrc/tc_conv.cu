@@ -335,13 +335,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const uint32_t b_base = ((a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE) >> 4) | B_LBO;
                     constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
                     if constexpr (TAPS == 9) {
+                        bool paired = false;
+                        if constexpr (2 * N <= 256) paired = a.pair != 0;
+                        if (paired) {
+                            // Paired issue: the view of halo rows 2j, 2j+1 is the dy=0 operand of accumulator j AND the dy=2
+                            // operand of accumulator j-1, whose TMEM columns are adjacent -- one 2N-column MMA against
+                            // [W_dy2 | W_dy0] replaces two N-column ones (A is fetched from shared memory once instead of
+                            // twice; 2*MT+1 MMAs per kernel column instead of 3*MT).  Weight block of (kc, dx):
+                            // [half][3N rows: dy2 | dy0 | dy1][8] (to_paired_layout).
+                            if constexpr (2 * N <= 256) {
+                                constexpr uint32_t B3_LBO = ((uint32_t)(3 * N * 16) >> 4) << 16;
+                                constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                const uint32_t b_addr = a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE;
 #pragma unroll
-                        for (int tap = 0; tap < 9; tap++) {
-                            const int dy = tap / 3, dx = tap - dy * 3;
-                            const uint32_t b_lo = b_base + (uint32_t)(tap * (2 * N * 16) >> 4);
-                            const uint32_t a_lo = a_base + (uint32_t)(((dy * TWP + dx) * 16) >> 4);
-                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
-                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                                for (int dx = 0; dx < 3; dx++) {
+                                    const uint32_t b_lo = ((b_addr + (uint32_t)(dx * (2 * 3 * N * 16))) >> 4) | B3_LBO;
+                                    const uint32_t a_lo = a_base + (uint32_t)dx;
+                                    if (nplanes == 2) {
+                                        umma_issue_pair<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, idesc2, 1u);
+                                        umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo + (uint32_t)TWP, b_lo + (uint32_t)(2 * N), DESC_HI, idesc, 1u);
+                                    } else {
+                                        umma_issue_pair<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, idesc2, 1u);
+                                        umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo + (uint32_t)TWP, b_lo + (uint32_t)(2 * N), DESC_HI, idesc, 1u);
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; tap++) {
+                                const int dy = tap / 3, dx = tap - dy * 3;
+                                const uint32_t b_lo = b_base + (uint32_t)(tap * (2 * N * 16) >> 4);
+                                const uint32_t a_lo = a_base + (uint32_t)(((dy * TWP + dx) * 16) >> 4);
+                                if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                                else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                            }
                         }
                         if (a.res_mode == 3) {
                             constexpr uint32_t I_LBO = ((uint32_t)(IROWS * 16) >> 4) << 16;
@@ -760,6 +787,7 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     if (ident_ok && a.res_mode == 1 && a.epi == TC_EPI_C8 && !a.s2 && a.res == (const __half*)in && a.Cin == a.N && a.Cout == a.N && a.N <= 128 && (!a.res_split) == (!a.split_in) &&
         (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
         a.res_mode = 3;
+    a.pair = (!a.s2 && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
     cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
@@ -840,8 +868,29 @@ void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int 
 }
 
 // ---- weight packing (host) -----------------------------------------------------------------------
+// Paired MMA issue (kernel: a.pair): RIFE_B200_PAIR=1 selects it for every stride-1 layer whose 2N fits one MMA.  The
+// switch is read once per process; packing and launching consult the same function, so they cannot disagree.
+bool tc_pair_enabled(int N) {
+    static const bool on = getenv("RIFE_B200_PAIR") ? atoi(getenv("RIFE_B200_PAIR")) != 0 : TC_PAIR_DEFAULT;
+    return on && 2 * N <= 256;
+}
+// [kc][tap = dy*3+dx][half][N][8] -> [kc][dx][half][3N rows: dy2 | dy0 | dy1][8]
+static void to_paired_layout(std::vector<uint16_t>& w, int kcs, int N) {
+    std::vector<uint16_t> o(w.size());
+    static const int slot[3] = {1, 2, 0};  // row block of dy = 0, 1, 2
+    for (int kc = 0; kc < kcs; kc++)
+        for (int dy = 0; dy < 3; dy++)
+            for (int dx = 0; dx < 3; dx++)
+                for (int hf = 0; hf < 2; hf++)
+                    for (int n = 0; n < N; n++) {
+                        const size_t src = ((((size_t)kc * 9 + dy * 3 + dx) * 2 + hf) * N + n) * 8;
+                        const size_t dst = ((((size_t)kc * 3 + dx) * 2 + hf) * (3 * N) + (size_t)slot[dy] * N + n) * 8;
+                        for (int j = 0; j < 8; j++) o[dst + j] = w[src + j];
+                    }
+    w.swap(o);
+}
 // conv: w[oc][ic][3][3] fp32 (fp16-exact) -> wpk[kc][tap][half][n][8] fp16, n = oc (zero padded to N)
-void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out) {
+void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out, int paired) {
     out.assign((size_t)(cin / 16) * 9 * 2 * N * 8, 0);
     for (int kc = 0; kc < cin / 16; kc++)
         for (int tap = 0; tap < 9; tap++)
@@ -852,6 +901,7 @@ void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<
                         __half h = __float2half_rn(w[((size_t)n * cin + ic) * 9 + tap]);
                         out[((((size_t)kc * 9 + tap) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
                     }
+    if (paired < 0 ? tc_pair_enabled(N) : (paired != 0 && 2 * N <= 256)) to_paired_layout(out, cin / 16, N);
 }
 // conv 3x3 stride 2: w[oc][ic][3][3] -> wpk[4 parities][cinp/16][4 slots][2][N][8]; parity (py,px) of the space-to-depth
 // input, slot (iy*2+ix) <-> tap dy = py ? 2*iy : 1, dx = px ? 2*ix : 1; input channels zero padded to cinp
@@ -877,7 +927,7 @@ void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, 
 }
 // deconv 4x4 s2 p1: w[oc][ic][4][4] -> 3x3-neighbourhood GEMM with n = parity*ocs + oc:
 // out(2y+py, 2x+px) = sum_{dy,dx} in(y-1+dy, x-1+dx) * w[oc][ic][3+py-2dy][3+px-2dx]  for dy-py, dx-px in {0,1}
-void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out) {
+void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out, int paired) {
     out.assign((size_t)(cin / 16) * 9 * 2 * N * 8, 0);
     for (int kc = 0; kc < cin / 16; kc++)
         for (int dy = 0; dy < 3; dy++)
@@ -894,6 +944,7 @@ void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, s
                                 out[((((size_t)kc * 9 + dy * 3 + dx) * 2 + hf) * N + par * ocs + oc) * 8 + j] = __half_as_ushort(h);
                             }
                 }
+    if (paired < 0 ? tc_pair_enabled(N) : (paired != 0 && 2 * N <= 256)) to_paired_layout(out, cin / 16, N);
 }
 
 }  // namespace rife

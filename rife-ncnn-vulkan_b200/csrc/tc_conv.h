@@ -34,6 +34,7 @@ struct TcConvArgs {
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
+    int pair;                       // filled by the launcher: paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled)
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
     int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
     int dbg_flags;                  // timing experiments only: 8 = empty epilogue (results wrong), 64 = one extra tcgen05.commit per stage
@@ -42,12 +43,17 @@ struct TcConvArgs {
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
 int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st);
 int tc_conv_tile_rows(int N);
+// Paired MMA issue for stride-1 layers with 2N <= 256 (environment RIFE_B200_PAIR, default TC_PAIR_DEFAULT): the
+// weight packers and the launcher both consult it.
+constexpr bool TC_PAIR_DEFAULT = false;
+bool tc_pair_enabled(int N);
 
 void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
 void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
 
-void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out);
+// paired: -1 = as tc_pair_enabled(N) says (what the launcher will assume), 0 / 1 = explicit (diagnostics)
+void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out, int paired = -1);
 void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, std::vector<uint16_t>& out);
-void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out);
+void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out, int paired = -1);
 
 }  // namespace rife
