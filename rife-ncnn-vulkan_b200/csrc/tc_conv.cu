@@ -251,7 +251,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         }
         *reinterpret_cast<uint4*>(biasB + (size_t)i * 8) = z;
     }
-    if (a.res_mode == 3) {
+    if (a.res_mode == 3 && (a.pair & 2)) {
+        // narrow identity tap: a 16 x 16 identity [half][16 rows][8]; the MMA of K chunk kc targets only the 16 accumulator
+        // columns of that chunk's channels (N = 16 instead of N: a quarter of the B bytes, a quarter of the math)
+        for (int i = threadIdx.x; i < 2 * 16 * 8; i += NTHREADS) {
+            const int j = i & 7, r = (i >> 3) & 15, hf = i >> 7;
+            ident[i] = __float2half_rn(r == hf * 8 + j ? 1.f : 0.f);
+        }
+    } else if (a.res_mode == 3) {
         for (int i = threadIdx.x; i < 2 * IROWS * 8; i += NTHREADS) {
             const int j = i & 7, r = (i >> 3) % IROWS, hf = (i >> 3) / IROWS;
             ident[i] = __float2half_rn(r - (N - 16) == hf * 8 + j ? 1.f : 0.f);
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
                     if constexpr (TAPS == 9) {
                         bool paired = false;
-                        if constexpr (2 * N <= 256) paired = a.pair != 0;
+                        if constexpr (2 * N <= 256) paired = (a.pair & 1) != 0;
                         if (paired) {
                             // Paired issue: the view of halo rows 2j, 2j+1 is the dy=0 operand of accumulator j AND the dy=2
                             // operand of accumulator j-1, whose TMEM columns are adjacent -- one 2N-column MMA against
@@ -370,7 +377,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                             }
                         }
-                        if (a.res_mode == 3) {
+                        if (a.res_mode == 3 && (a.pair & 2)) {
+                            constexpr uint32_t I16_LBO = ((uint32_t)(16 * 16) >> 4) << 16;
+                            constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                            const uint32_t b_lo = (smem_u32(ident) >> 4) | I16_LBO;
+                            const uint32_t a_lo = a_base + (uint32_t)(((1 * TWP + 1) * 16) >> 4);
+                            const uint32_t accn = acc0 + (uint32_t)(16 * kc);
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
+                        } else if (a.res_mode == 3) {
                             constexpr uint32_t I_LBO = ((uint32_t)(IROWS * 16) >> 4) << 16;
                             const uint32_t b_lo = ((smem_u32(ident) + (uint32_t)((N - 16 - 16 * kc) * 16)) >> 4) | I_LBO;
                             const uint32_t a_lo = a_base + (uint32_t)(((1 * TWP + 1) * 16) >> 4);
@@ -788,6 +803,10 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
         (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
         a.res_mode = 3;
     a.pair = (!a.s2 && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
+    {   // bit 1 (RIFE_B200_PAIR=2 / 3): narrow identity tap for the self-residual layers, independent of the weight layout
+        static const int pm = getenv("RIFE_B200_PAIR") ? atoi(getenv("RIFE_B200_PAIR")) : (TC_PAIR_DEFAULT ? 1 : 0);
+        if (pm & 2) a.pair |= 2;
+    }
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
     cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
@@ -871,7 +890,7 @@ void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int 
 // Paired MMA issue (kernel: a.pair): RIFE_B200_PAIR=1 selects it for every stride-1 layer whose 2N fits one MMA.  The
 // switch is read once per process; packing and launching consult the same function, so they cannot disagree.
 bool tc_pair_enabled(int N) {
-    static const bool on = getenv("RIFE_B200_PAIR") ? atoi(getenv("RIFE_B200_PAIR")) != 0 : TC_PAIR_DEFAULT;
+    static const bool on = getenv("RIFE_B200_PAIR") ? (atoi(getenv("RIFE_B200_PAIR")) & 1) != 0 : TC_PAIR_DEFAULT;
     return on && 2 * N <= 256;
 }
 // [kc][tap = dy*3+dx][half][N][8] -> [kc][dx][half][3N rows: dy2 | dy0 | dy1][8]

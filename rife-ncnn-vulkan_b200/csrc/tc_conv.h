@@ -34,7 +34,7 @@ struct TcConvArgs {
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
-    int pair;                       // filled by the launcher: paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled)
+    int pair;                       // filled by the launcher: bit 0 paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled), bit 1 narrow identity tap
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
     int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
     int dbg_flags;                  // timing experiments only: 8 = empty epilogue (results wrong), 64 = one extra tcgen05.commit per stage
