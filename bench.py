@@ -322,8 +322,16 @@ def main():
     achieved = flop / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md)
     # (single-image captures, scaled by the images per launch: the kernel re-reads nothing across images)
-    traffic = ({(272, 480): 34.4e6, (544, 960): 242.3e6} if split else {(272, 480): 16.9e6, (544, 960): 89.7e6}).get((ch, cw))
-    traffic = traffic * kb if traffic else None
+    # keyed "<w>x<h>x<images>_<split|plain>" -> dram__bytes_read.sum + dram__bytes_write.sum of one launch
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "conv64_dram_traffic.json")))
+        traffic = tj.get("%dx%dx%d_%s" % (cw, ch, kb, "split" if split else "plain"))
+        if traffic is None:  # single-image capture scaled by the images per launch (the kernel re-reads nothing across images)
+            one = tj.get("%dx%dx1_%s" % (cw, ch, "split" if split else "plain"))
+            traffic = one * kb if one else None
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
                 "kernel": "tc_conv3x3_kernel<64,4,3,9> %d x %dx%d" % (kb, cw, ch), "images_per_launch": kb, "us_per_launch": k_ms * 1000.0, "peak_source": how + " bf16 burst",
                 "tensor_issue_multiplier": 2 if split else 1}

@@ -37,6 +37,8 @@ struct Lane {
     void release();
 };
 
+constexpr int RECOMPUTE_FM_DEFAULT = 0;
+
 class Engine {
 public:
     Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v4);
@@ -71,7 +73,7 @@ private:
     bool fast_ok_ = false;  // the fused v4.6 path reproduced the generic executor on the self-check
     int use_fast_ = 1;
     int plain_mask_ = 12;  // IFBlocks 2 and 3 (80 % of the FLOPs): plain fp16 activations in the residual chain (profiles/r1_precision_study_plain_blocks.txt)
-    int recompute_fm_ = 0;  // fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2: fused_v46.h)
+    int recompute_fm_ = RECOMPUTE_FM_DEFAULT;  // fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2: fused_v46.h)
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;
     Net nets_[3];           // flownet, contextnet, fusionnet
