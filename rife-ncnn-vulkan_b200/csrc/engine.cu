@@ -198,6 +198,7 @@ int Engine::set_option(const std::string& key, int value) {
     }
     if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
+    if (key == "combine") { combine_ = value != 0; return 0; }
     if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
     last_error = "unknown option " + key;
     return -1;
@@ -211,6 +212,9 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "batch") *value = batch_;
     else if (key == "plain_blocks") *value = plain_mask_;
     else if (key == "recompute_fm") *value = recompute_fm_;
+    else if (key == "combine") *value = combine_;
+    else if (key == "combined_batches") *value = (int)combiner_.batches();
+    else if (key == "combined_requests") *value = (int)combiner_.requests();
     else if (key == "fast_active") *value = fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1;
     else { last_error = "unknown option " + key; return -1; }
     return 0;
@@ -314,7 +318,33 @@ int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, f
     const uint8_t* b[1] = {in1};
     uint8_t* o[1] = {out};
     if (!in0 || !in1 || !out) { last_error = "bad argument"; return -1; }
+    // The reference's CLI calls process() from several proc threads on one object (src/main.cpp:346-366): requests that
+    // arrive while another is being served are executed together as one lock-step batch instead of one after the other.
+    if (combine_ && loaded_ && w > 0 && h > 0 && batch_for(w, h) > 1) {
+        HostReq r = {in0, in1, w, h, t, out};
+        int cap = batch_for(w, h) * (int)lanes_.size();
+        return combiner_.submit(&r, cap, [this](HostReq** rq, int n) { return run_combined(rq, n); });
+    }
     return process_batch(1, a, b, w, h, &t, o);
+}
+
+// n queued process() calls: one process_batch per run of equal frame size (a real caller has a single size)
+int Engine::run_combined(HostReq** rq, int n) {
+    const uint8_t* a[Combiner<HostReq>::kMax];
+    const uint8_t* b[Combiner<HostReq>::kMax];
+    uint8_t* o[Combiner<HostReq>::kMax];
+    float ts[Combiner<HostReq>::kMax];
+    int rc = 0;
+    for (int i = 0; i < n;) {
+        int j = i;
+        for (; j < n && rq[j]->w == rq[i]->w && rq[j]->h == rq[i]->h; j++) {
+            a[j - i] = rq[j]->in0; b[j - i] = rq[j]->in1; o[j - i] = rq[j]->out; ts[j - i] = rq[j]->t;
+        }
+        const int r = process_batch(j - i, a, b, rq[i]->w, rq[i]->h, ts, o);
+        if (r) rc = r;
+        i = j;
+    }
+    return rc;
 }
 
 int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out) {

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "combiner.h"
 #include "exec.h"
 #include "fused_v46.h"
 #include "model.h"
@@ -38,6 +39,7 @@ struct Lane {
 };
 
 constexpr int RECOMPUTE_FM_DEFAULT = 0;
+constexpr int COMBINE_DEFAULT = 0;
 
 class Engine {
 public:
@@ -52,6 +54,13 @@ public:
     int process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out);
     int process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out);
     int set_option(const std::string& key, int value);
+    struct HostReq {  // one process() call waiting in the combiner
+        const uint8_t* in0;
+        const uint8_t* in1;
+        int w, h;
+        float t;
+        uint8_t* out;
+    };
     int get_option(const std::string& key, int* value);
     void set_stream(cudaStream_t s) { std::lock_guard<std::mutex> lk(mu_); user_stream_ = s; use_user_stream_ = s != nullptr; }
     std::string last_error;
@@ -73,6 +82,9 @@ private:
     bool fast_ok_ = false;  // the fused v4.6 path reproduced the generic executor on the self-check
     int use_fast_ = 1;
     int plain_mask_ = 12;  // IFBlocks 2 and 3 (80 % of the FLOPs): plain fp16 activations in the residual chain (profiles/r1_precision_study_plain_blocks.txt)
+    int combine_ = COMBINE_DEFAULT;  // concurrent process() calls on this handle are executed as one lock-step batch (combiner.h)
+    Combiner<HostReq> combiner_;
+    int run_combined(HostReq** rq, int n);
     int recompute_fm_ = RECOMPUTE_FM_DEFAULT;  // fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2: fused_v46.h)
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;

@@ -244,3 +244,41 @@ def test_v46_recompute_fm_modes_are_bit_identical(pkg, w, h):
     for mode in (1, 2):
         for a_, b_ in zip(results[0], results[mode]):
             assert np.array_equal(a_, b_), (mode, parity.compare(a_, b_))
+
+
+def test_concurrent_process_calls_are_combined_into_batches(pkg):
+    """Option "combine": process() calls arriving from several threads while another call is being served run as one
+    lock-step batch (csrc/combiner.h) -- the reference CLI's `-j load:proc:save` threading (src/main.cpp:346-366).
+    Results must equal the one-at-a-time results bit for bit, and some batching must actually have happened."""
+    _need("rife-v4.6")
+    import threading
+    w, h = 320, 192
+    frames = [parity.synth.frame(k, w, h) for k in range(9)]
+    v2, v4 = pkg.family_flags("rife-v4.6")
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir("rife-v4.6"))
+    expect = [r.process(frames[i], frames[i + 1], 0.5) for i in range(8)]
+    r.set_option("combine", 1)
+    got = [None] * 8
+    errs = []
+    gate = threading.Barrier(8)
+
+    def work(i):
+        try:
+            gate.wait()
+            for _ in range(4):
+                got[i] = r.process(frames[i], frames[i + 1], 0.5)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    nb, nr = r.get_option("combined_batches"), r.get_option("combined_requests")
+    r.close()
+    assert not errs, errs
+    for e, g_ in zip(expect, got):
+        assert np.array_equal(e, g_)
+    assert nr == 32 and nb < nr, (nb, nr)
