@@ -30,6 +30,7 @@ Engine::Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v
     : gpuid_(gpuid), tta_(tta), ttat_(tta_temporal), uhd_(uhd), v2_(v2), v4_(v4) {
     // process-wide default of option "recompute_fm" (lets a whole test run exercise one setting)
     if (const char* e = getenv("RIFE_B200_RECOMPUTE_FM")) { int v = atoi(e); recompute_fm_ = v < 0 ? 0 : (v > 2 ? 2 : v); }
+    if (const char* e = getenv("RIFE_B200_COMBINE")) combine_ = atoi(e) != 0;
 }
 
 void Lane::release() {

@@ -803,10 +803,7 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
         (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
         a.res_mode = 3;
     a.pair = (!a.s2 && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
-    {   // bit 1 (RIFE_B200_PAIR=2 / 3): narrow identity tap for the self-residual layers, independent of the weight layout
-        static const int pm = getenv("RIFE_B200_PAIR") ? atoi(getenv("RIFE_B200_PAIR")) : (TC_PAIR_DEFAULT ? 1 : 0);
-        if (pm & 2) a.pair |= 2;
-    }
+    if (tc_pair_mode() & 2) a.pair |= 2;  // narrow identity tap for the self-residual layers (independent of the weight layout)
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
     cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
@@ -887,12 +884,16 @@ void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int 
 }
 
 // ---- weight packing (host) -----------------------------------------------------------------------
-// Paired MMA issue (kernel: a.pair): RIFE_B200_PAIR=1 selects it for every stride-1 layer whose 2N fits one MMA.  The
-// switch is read once per process; packing and launching consult the same function, so they cannot disagree.
-bool tc_pair_enabled(int N) {
-    static const bool on = getenv("RIFE_B200_PAIR") ? (atoi(getenv("RIFE_B200_PAIR")) & 1) != 0 : TC_PAIR_DEFAULT;
-    return on && 2 * N <= 256;
+// Paired MMA issue (kernel: a.pair), for every stride-1 layer whose 2N fits one MMA.  RIFE_B200_PAIR (bit 0: paired
+// issue + [dy2|dy0|dy1] weight blocks, bit 1: narrow identity tap; default TC_PAIR_DEFAULT) is read once per process;
+// packing and launching consult the same function, so they cannot disagree.
+// Measured (profiles/README.md, round-1 session 20): 16-channel mainloop stage of the 64->64 layer 2306 -> 1979 cycles,
+// the layer itself 96.5 -> 84.2 us at 8 x 480x272, whole model 2195 -> 2311 frames/s at 1080p.
+int tc_pair_mode() {
+    static const int mode = getenv("RIFE_B200_PAIR") ? atoi(getenv("RIFE_B200_PAIR")) & 3 : TC_PAIR_DEFAULT;
+    return mode;
 }
+bool tc_pair_enabled(int N) { return (tc_pair_mode() & 1) && 2 * N <= 256; }
 // [kc][tap = dy*3+dx][half][N][8] -> [kc][dx][half][3N rows: dy2 | dy0 | dy1][8]
 static void to_paired_layout(std::vector<uint16_t>& w, int kcs, int N) {
     std::vector<uint16_t> o(w.size());

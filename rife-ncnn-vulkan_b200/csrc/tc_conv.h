@@ -43,9 +43,10 @@ struct TcConvArgs {
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
 int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st);
 int tc_conv_tile_rows(int N);
-// Paired MMA issue for stride-1 layers with 2N <= 256 (environment RIFE_B200_PAIR, default TC_PAIR_DEFAULT): the
-// weight packers and the launcher both consult it.
-constexpr bool TC_PAIR_DEFAULT = false;
+// Paired MMA issue for stride-1 layers with 2N <= 256 (environment RIFE_B200_PAIR: bit 0 paired issue, bit 1 narrow
+// identity tap; default TC_PAIR_DEFAULT): the weight packers and the launcher both consult it.
+constexpr int TC_PAIR_DEFAULT = 3;
+int tc_pair_mode();
 bool tc_pair_enabled(int N);
 
 void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
