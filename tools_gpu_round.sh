@@ -42,7 +42,7 @@ RIFE_BENCH_PAIRS=8 timeout 240 ncu --metrics gpu__time_duration.sum --clock-cont
     python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline > $O/ncu_launches.log 2>&1
 stamp "ncu launch list rc=$?"
 RIFE_BENCH_PAIRS=8 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:(tc_conv3x3_kernel<32, 4, 4, 4>|head_update_kernel<1, 2, 2, 8|head_update_kernel<2, 4, 1, 8|tail_kernel)' -s 8 -c 8 -f -o $O/block3_hbm \
+    -k 'regex:(tc_conv3x3_kernel<32, 4, 4, 4>|head_update_kernel<1, 2, 2, 8|head_update_kernel<2, 4, 1, 8|tail_kernel)' -s 10 -c 10 -f -o $O/block3_hbm \
     python bench.py --steps 1 --warmup 3 --lanes 1 --no-cpu-baseline > $O/ncu_block3.log 2>&1
 timeout 60 ncu -i $O/block3_hbm.ncu-rep --page details --csv > $O/block3_hbm_details.csv 2>> $O/ncu_block3.log
 stamp "ncu block-3 captures rc=$?"
