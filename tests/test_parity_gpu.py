@@ -257,8 +257,10 @@ def test_concurrent_process_calls_are_combined_into_batches(pkg):
     v2, v4 = pkg.family_flags("rife-v4.6")
     r = pkg.RIFE(0, False, False, False, 1, v2, v4)
     r.load(parity.model_dir("rife-v4.6"))
+    r.set_option("combine", 0)
     expect = [r.process(frames[i], frames[i + 1], 0.5) for i in range(8)]
     r.set_option("combine", 1)
+    nb0, nr0 = r.get_option("combined_batches"), r.get_option("combined_requests")
     got = [None] * 8
     errs = []
     gate = threading.Barrier(8)
@@ -276,7 +278,7 @@ def test_concurrent_process_calls_are_combined_into_batches(pkg):
         t.start()
     for t in ts:
         t.join()
-    nb, nr = r.get_option("combined_batches"), r.get_option("combined_requests")
+    nb, nr = r.get_option("combined_batches") - nb0, r.get_option("combined_requests") - nr0
     r.close()
     assert not errs, errs
     for e, g_ in zip(expect, got):
