@@ -70,7 +70,9 @@ int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned ch
  * convolutions with split-precision operands where needed).  Default 1 when the model supports it. */
 /* other keys: "lanes" (1-4 concurrent streams), "batch" (pairs per lock-step batch on the fused path, 0 = auto),
  * "plain_blocks" (bit k: IFBlock k's residual chain uses plain fp16 activations instead of split hi+lo; default 12),
- * "fast" (0/1 fused rife-v4.6 path), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path) */
+ * "fast" (0/1 fused rife-v4.6 path), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path),
+ * "combine" (0/1, default 1: concurrent rife_b200_process calls on one handle run as one lock-step batch),
+ * "recompute_fm" (0-2, default 0: fused path rebuilds the full-resolution flow / mask planes instead of storing them) */
 int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
 /* reads back "precision", "lanes", "fast" (requested) and "fast_active" (1 when the fused rife-v4.6 path passed its
  * load-time self-check against the generic executor and is the one process() runs) */
