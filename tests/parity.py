@@ -66,8 +66,9 @@ def port_binary():
     return p if os.path.exists(p) else None
 
 
-def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd=False, threads=None, repeat=1, warmup=0, which="auto"):
-    """Returns (out u8 array, info dict).  which: 'ref' | 'port' | 'auto' (ref if present else port)."""
+def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd=False, threads=None, repeat=1, warmup=0, which="auto", modeldir=None):
+    """Returns (out u8 array, info dict).  which: 'ref' | 'port' | 'auto' (ref if present else port).
+    modeldir overrides the lookup of `model` (the family flags still come from the name)."""
     exe = None
     kind = None
     if which in ("auto", "ref"):
@@ -78,7 +79,7 @@ def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd
         kind = "port"
     if exe is None:
         raise RuntimeError("no oracle executable available (oracle/_ref/ref_rife_* or oracle/build/oracle_rife)")
-    md = model_dir(model)
+    md = modeldir or model_dir(model)
     if md is None:
         raise RuntimeError("model %s not available" % model)
     h, w = in0.shape[:2]

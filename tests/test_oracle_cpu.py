@@ -75,3 +75,25 @@ def test_synthetic_model_loads_in_both_oracles(tmp_path):
     assert outs[0].std() > 5
     if len(outs) == 2:
         assert np.abs(outs[0].astype(int) - outs[1].astype(int)).max() <= 1
+
+
+ALL_FAMILIES = ["rife", "rife-HD", "rife-UHD", "rife-anime", "rife-v2", "rife-v2.3", "rife-v2.4", "rife-v3.0", "rife-v3.1", "rife-v4", "rife-v4.6"]
+
+
+@pytest.mark.parametrize("model", ALL_FAMILIES)
+def test_port_matches_reference_binary_for_every_model_directory(model):
+    """Every model directory the reference ships, read from the reference tree where it is
+    mounted: the C++ restatement against the reference's own CPU path.  Build-container only (the GPU box has neither the
+    tree nor a need for it)."""
+    md = os.path.join("/root/reference/models", model)
+    if not os.path.isdir(md):
+        pytest.skip("reference tree not mounted")
+    if parity.ref_binary() is None or parity.port_binary() is None:
+        pytest.skip("oracle executables not built")
+    a, b = parity.synth.pair(96, 64)
+    t = 0.25 if parity.FAMILY[model] == "v4" else 0.5
+    ref, _ = parity.run_oracle(model, a, b, t, which="ref", modeldir=md, threads=4)
+    port, _ = parity.run_oracle(model, a, b, t, which="port", modeldir=md, threads=4)
+    res = parity.compare(port, ref)
+    assert ref.std() > 5
+    assert res["max_abs_diff"] <= 1 and res["share_ne"] < 2e-3, res
