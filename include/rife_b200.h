@@ -112,6 +112,12 @@ int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w
                             const float* weight, const float* bias, const float* res, float slope, float* out_tc,
                             float* out_ref);
 
+/* Diagnostics (host only, no GPU): parses one network (<name>.param + <name>.bin, the reference's model format:
+ * src/ncnn/src/net.cpp:1374-1590, modelbin.cpp:89-260) and reports its layer / blob / weight-value counts; on failure
+ * returns RIFE_B200_ERR_MODEL with the loader's message in `err` (may be NULL). */
+int rife_b200_debug_parse_model(const char* param_path, const char* bin_path, int* layers, int* blobs,
+                                unsigned long long* weight_values, char* err, int err_len);
+
 /* Diagnostics (host only, no GPU): the weight packing of the tcgen05 kernel, fp16 bit patterns.
  * mode 0: conv3x3 w[cout][cin][3][3]; mode 1: deconv4x4 s2 w[cout][cin][4][4] with `ocs` column slots per output parity.
  * out_elems must be (cin/16)*9*2*N*8.  paired: 0 = [kc][tap][half][N][8]; 1 = [kc][dx][half][3N: dy2|dy0|dy1][8]

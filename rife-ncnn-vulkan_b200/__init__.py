@@ -44,6 +44,7 @@ def lib():
     L.rife_b200_bench_conv.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci]
     L.rife_b200_bench_conv_batched.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, ci]
     L.rife_b200_selftest_conv.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, cf, vp, vp]
+    L.rife_b200_debug_parse_model.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_char_p, ci]
     L.rife_b200_debug_pack_weights.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, ctypes.c_size_t]
     L.rife_b200_launch_count.restype = ctypes.c_ulonglong
     L.rife_b200_h2d_bytes.restype = ctypes.c_ulonglong
@@ -59,7 +60,7 @@ def lib():
 EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
            "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_get_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv", "rife_b200_bench_conv_batched",
-           "rife_b200_debug_conv_timeline", "rife_b200_debug_pack_weights",
+           "rife_b200_debug_conv_timeline", "rife_b200_debug_pack_weights", "rife_b200_debug_parse_model",
            "rife_b200_launch_count", "rife_b200_h2d_bytes", "rife_b200_d2h_bytes", "rife_b200_last_error", "rife_b200_destroy"]
 
 

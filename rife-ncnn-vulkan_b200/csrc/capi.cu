@@ -310,6 +310,25 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     GUARD_END
 }
 
+// diagnostics (host only, no GPU needed): parse one network of a model directory
+extern "C" int rife_b200_debug_parse_model(const char* param_path, const char* bin_path, int* layers, int* blobs, unsigned long long* weight_values,
+                                           char* err, int err_len) {
+    GUARD_BEGIN
+    if (!param_path || !bin_path) return RIFE_B200_ERR_ARG;
+    rife::Net net;
+    std::string e;
+    int r = rife::load_net(param_path, bin_path, net, e);
+    if (err && err_len > 0) { snprintf(err, (size_t)err_len, "%s", e.c_str()); }
+    if (r) return RIFE_B200_ERR_MODEL;
+    unsigned long long nv = 0;
+    for (const rife::Layer& L : net.layers) nv += L.weight.size() + L.bias.size() + L.slope.size();
+    if (layers) *layers = (int)net.layers.size();
+    if (blobs) *blobs = (int)net.blob_names.size();
+    if (weight_values) *weight_values = nv;
+    return 0;
+    GUARD_END
+}
+
 // diagnostics (host only, no GPU needed): the tensor-core weight packing, so a CPU test can replay the MMA operand views
 extern "C" int rife_b200_debug_pack_weights(int mode, int cout, int cin, int N, int ocs, int paired, const float* w, unsigned short* out, size_t out_elems) {
     GUARD_BEGIN

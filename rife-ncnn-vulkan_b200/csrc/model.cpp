@@ -80,6 +80,7 @@ struct BinReader {
     bool tagged(size_t n, std::vector<float>& out, bool& fp16) {
         uint32_t tag;
         if (!take(&tag, 4)) return false;
+        if (n > d.size()) { ok = false; return false; }  // a count from a damaged .param must not drive the allocation below
         out.resize(n);
         if (tag == 0x01306B47u) {  // fp16 payload padded to 4 bytes
             fp16 = true;
@@ -101,6 +102,7 @@ struct BinReader {
         return false;
     }
     bool raw(size_t n, std::vector<float>& out) {
+        if (n > d.size() / 4 || pos + n * 4 > d.size()) { ok = false; return false; }
         out.resize(n);
         return n == 0 || take(out.data(), n * 4);
     }
@@ -144,9 +146,16 @@ int parse_net(const std::string& param_text, const std::string& bin_bytes, const
         Layer L;
         int nbot = 0, ntop = 0;
         if (!(ss >> L.type >> L.name >> nbot >> ntop)) continue;
+        if (nbot < 0 || ntop < 0 || nbot > 4096 || ntop > 4096) { err = "bad blob counts at layer " + L.name + " in " + param_path; return -2; }
         std::string tok;
-        for (int i = 0; i < nbot; i++) { ss >> tok; L.bottoms.push_back(blob(tok)); }
-        for (int i = 0; i < ntop; i++) { ss >> tok; L.tops.push_back(blob(tok)); }
+        for (int i = 0; i < nbot; i++) {
+            if (!(ss >> tok)) { err = "missing bottom blob at layer " + L.name + " in " + param_path; return -2; }
+            L.bottoms.push_back(blob(tok));
+        }
+        for (int i = 0; i < ntop; i++) {
+            if (!(ss >> tok)) { err = "missing top blob at layer " + L.name + " in " + param_path; return -2; }
+            L.tops.push_back(blob(tok));
+        }
         while (ss >> tok) {
             size_t eq = tok.find('=');
             if (eq == std::string::npos) continue;
@@ -182,6 +191,7 @@ int parse_net(const std::string& param_text, const std::string& bin_bytes, const
         net.layers.push_back(L);
     }
     if ((int)net.layers.size() != nl) { err = "layer count mismatch in " + param_path; return -2; }
+    if ((int)net.blob_names.size() > nb) { err = "more blobs than declared in " + param_path; return -2; }
     net.producer.assign(net.blob_names.size(), -1);
     for (size_t li = 0; li < net.layers.size(); li++)
         for (int t : net.layers[li].tops) net.producer[t] = (int)li;
@@ -193,10 +203,15 @@ int parse_net(const std::string& param_text, const std::string& bin_bytes, const
             int num_output = L.geti(0, 0);
             bool has_bias = L.type == "InnerProduct" ? L.geti(1, 0) != 0 : L.geti(5, 0) != 0;
             int wsize = L.type == "InnerProduct" ? L.geti(2, 0) : L.geti(6, 0);
-            br.tagged((size_t)wsize, L.weight, L.weight_is_fp16);
-            if (has_bias) br.raw((size_t)num_output, L.bias);
+            if (wsize < 0 || num_output < 0) br.ok = false;
+            else {
+                br.tagged((size_t)wsize, L.weight, L.weight_is_fp16);
+                if (br.ok && has_bias) br.raw((size_t)num_output, L.bias);
+            }
         } else if (L.type == "PReLU") {
-            br.raw((size_t)L.geti(0, 0), L.slope);
+            int ns = L.geti(0, 0);
+            if (ns < 0) br.ok = false;
+            else br.raw((size_t)ns, L.slope);
         }
         if (!br.ok) { err = "truncated or unsupported weights in " + bin_path + " at layer " + L.name; return -3; }
     }
