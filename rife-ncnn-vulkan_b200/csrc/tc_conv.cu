@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "tc_conv.h"
@@ -760,12 +761,16 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     if (smem > 227 * 1024) return -2;
     // the attribute is per device: one process may drive several GPUs (src/main.cpp -g 0,1,...)
     static size_t configured[64] = {};
+    static std::mutex configured_mu;  // lanes of several engines / threads may launch the same instantiation for the first time together
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -3;
-    if (smem > configured[dev]) {
-        if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-        configured[dev] = smem;
+    {
+        std::lock_guard<std::mutex> lk(configured_mu);
+        if (smem > configured[dev]) {
+            if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+            configured[dev] = smem;
+        }
     }
     int ntiles = a.tiles_x * a.tiles_y * a.batch;
     int grid = ntiles < a.num_sms ? ntiles : a.num_sms;
