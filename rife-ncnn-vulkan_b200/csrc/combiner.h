@@ -43,7 +43,12 @@ public:
                 n++;
             }
             lk.unlock();
-            const int status = fn(reqs, n);
+            int status;
+            try {
+                status = fn(reqs, n);
+            } catch (...) {
+                status = kThrown;  // the batch function must not take the queue down with it: everyone gets an error, leadership moves on
+            }
             lk.lock();
             for (int i = 0; i < n; i++) { take[i]->status = status; take[i]->done = true; }
             batches_++;
@@ -59,6 +64,7 @@ public:
     unsigned long long requests() { std::lock_guard<std::mutex> lk(m_); return requests_; }
 
     static constexpr int kMax = 32;
+    static constexpr int kThrown = -1000;  // status handed to every request of a batch whose function threw
 
 private:
     struct Slot {

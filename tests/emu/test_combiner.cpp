@@ -50,6 +50,29 @@ int main() {
         printf("FAIL bad=%d overlap=%d requests=%llu max=%d\n", bad.load(), overlap.load(), nr, maxn.load());
         return 1;
     }
+    // a throwing batch function: every waiter gets the error status, the queue keeps working afterwards
+    {
+        std::atomic<int> thrown{0};
+        auto bad_fn = [&](Req** r, int n) -> int {
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+            if (r[0]->in < 0) { thrown++; throw 42; }
+            for (int i = 0; i < n; i++) r[i]->out = 7;
+            return 0;
+        };
+        std::vector<Req> rq(6);
+        std::vector<int> st2(6, 1);
+        std::vector<std::thread> t2;
+        for (int i = 0; i < 6; i++) {
+            rq[i].in = -1;
+            t2.emplace_back([&, i] { st2[i] = c.submit(&rq[i], 8, bad_fn); });
+        }
+        for (auto& x : t2) x.join();
+        for (int i = 0; i < 6; i++)
+            if (st2[i] != rife::Combiner<Req>::kThrown) { printf("FAIL throw status %d\n", st2[i]); return 1; }
+        Req ok;
+        ok.in = 1;
+        if (c.submit(&ok, 8, bad_fn) != 0 || ok.out != 7 || thrown.load() < 1) { printf("FAIL queue dead after throw\n"); return 1; }
+    }
     printf("COMBINER OK\n");
     return 0;
 }
