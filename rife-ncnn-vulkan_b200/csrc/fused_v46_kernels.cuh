@@ -18,10 +18,32 @@ namespace fusedk {
 // interp.cpp:54-91 (coefficient in double, rounded to float)
 // `scale` = in_n / out_n, which on this path is always an exact power of two (8, 4, 2, 1/2, 1/4, 1/8) known at compile
 // time, so the reference's double division is folded; the rest of the arithmetic is unchanged
+// RIFE_FUSED_LEAN = 1 (compile-time, default 0 until measured on the GPU): same results bit for bit with fewer
+// instructions on the slow pipes -- lin_coeff in integers instead of fp64 (every intermediate of the original is exactly
+// representable, so nothing is rounded either way), packed float->half conversions in the hi/lo split.  tests/emu checks
+// both builds against the whole-image restatement and against each other, exhaustively for lin_coeff.
+#ifndef RIFE_FUSED_LEAN
+#define RIFE_FUSED_LEAN 0
+#endif
 __device__ __forceinline__ void lin_coeff(int d, double scale, int in_n, int& s, float& f) {
+#if RIFE_FUSED_LEAN
+    int sx;
+    float fx;
+    if (scale >= 1.0) {  // down-sampling by k = 2, 4, 8: (d + 0.5) * k - 0.5 = d*k + (k/2 - 1) + 0.5
+        const int k = (int)scale;
+        sx = d * k + (k / 2 - 1);
+        fx = 0.5f;
+    } else {             // up-sampling by k: (d + 0.5) / k - 0.5 = (2d + 1 - k) / 2k
+        const int k2 = 2 * (int)(1.0 / scale + 0.5);  // 2k, a power of two
+        const int n = 2 * d + 1 - k2 / 2;
+        sx = n >= 0 ? n / k2 : -((k2 - 1 - n) / k2);   // floor(n / 2k)
+        fx = (float)(n - sx * k2) * (1.f / (float)k2);    // exact: numerator < 2k, 1/2k a power of two
+    }
+#else
     float fx = (float)((d + 0.5) * scale - 0.5);
     int sx = (int)floorf(fx);
     fx -= sx;
+#endif
     if (sx < 0) { sx = 0; fx = 0.f; }
     if (sx >= in_n - 1) { sx = in_n - 2; fx = 1.f; }
     s = sx;
@@ -98,15 +120,30 @@ __device__ __forceinline__ void store_c8_s2d_16(__half* out, const float* v, int
     const size_t pix = (size_t)(oy >> 1) * (ow >> 1) + (ox >> 1);
 #pragma unroll
     for (int g = 0; g < 2; g++) {
+        const size_t off = (((size_t)par * 2 + g) * sub + pix) * 8;
+#if RIFE_FUSED_LEAN
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // two channels per conversion (cvt.rn.f16x2.f32), same rounding as the scalar form
+            const float a = v[g * 8 + 2 * k], b = v[g * 8 + 2 * k + 1];
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            hw[k] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[k] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(out + plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+#else
         __half hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             hi[j] = __float2half_rn(v[g * 8 + j]);
             lo[j] = __float2half_rn(v[g * 8 + j] - __half2float(hi[j]));
         }
-        const size_t off = (((size_t)par * 2 + g) * sub + pix) * 8;
         *reinterpret_cast<uint4*>(out + off) = make_uint4(pack2h(hi[0], hi[1]), pack2h(hi[2], hi[3]), pack2h(hi[4], hi[5]), pack2h(hi[6], hi[7]));
         *reinterpret_cast<uint4*>(out + plane + off) = make_uint4(pack2h(lo[0], lo[1]), pack2h(lo[2], lo[3]), pack2h(lo[4], lo[5]), pack2h(lo[6], lo[7]));
+#endif
     }
 }
 

@@ -264,8 +264,32 @@ static void run_reference(const Case& c, int b, std::vector<float> xr[4], std::v
         }
 }
 
+static uint64_t fnv(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 int main(int argc, char** argv) {
     int fails = 0;
+    uint64_t sum = 1469598103934665603ull;
+    // lin_coeff of this build against the reference arithmetic (interp.cpp:54-91), exhaustively over the coordinates and scales in use
+    {
+        const double scales[6] = {8.0, 4.0, 2.0, 0.5, 0.25, 0.125};
+        const int sizes[5] = {2, 3, 34, 1088, 8192};
+        long bad = 0;
+        for (double sc : scales)
+            for (int in_n : sizes)
+                for (int d = 0; d < 8192; d++) {
+                    int s0, s1;
+                    float f0, f1;
+                    ref_lin(d, sc, in_n, s0, f0);
+                    lin_coeff(d, sc, in_n, s1, f1);
+                    if (s0 != s1 || memcmp(&f0, &f1, 4)) bad++;
+                }
+        printf("lin_coeff (RIFE_FUSED_LEAN=%d) vs reference arithmetic: %ld mismatches\n", RIFE_FUSED_LEAN, bad);
+        if (bad) fails++;
+    }
     const int sizes[][3] = {{64, 64, 2}, {100, 70, 3}, {160, 96, 1}, {96, 128, 2}};
     for (auto& sz : sizes) {
         Case c;
@@ -308,10 +332,13 @@ int main(int argc, char** argv) {
                 omax = std::max(omax, dd);
             }
         }
+        for (int k = 0; k < 4; k++) sum = fnv(sum, r0.x[k].data(), r0.x[k].size() * sizeof(__half));
+        sum = fnv(sum, r0.out.data(), r0.out.size());
         printf("%dx%d n=%d: head tensors vs restatement max rel err %.3g, output bytes differing %zu (max %zu)\n", sz[0], sz[1], sz[2], worst, odiff, omax);
         if (worst > 2e-6) { printf("FAIL %dx%d: head tensor mismatch\n", sz[0], sz[1]); fails++; }
         if (omax > 0) { printf("FAIL %dx%d: output mismatch\n", sz[0], sz[1]); fails++; }
     }
+    printf("checksum of all head tensors and frames: %016llx\n", (unsigned long long)sum);
     printf(fails ? "EMU FAILED (%d)\n" : "EMU OK\n", fails);
     return fails ? 1 : 0;
 }

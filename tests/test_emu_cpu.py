@@ -18,15 +18,26 @@ def _cuda_include():
     return None
 
 
-def test_fused_kernels_host_emulation(tmp_path):
+def _build_and_run(tmp_path, lean):
     inc = _cuda_include()
     if shutil.which("g++") is None or inc is None:
         pytest.skip("g++ or CUDA headers not available")
-    exe = str(tmp_path / "emu_fused")
+    exe = str(tmp_path / ("emu_fused_lean%d" % lean))
     src = os.path.join(ROOT, "tests", "emu", "emu_fused.cpp")
     csrc = os.path.join(ROOT, "rife-ncnn-vulkan_b200", "csrc")
     # -ffp-contract=off: every variant must round identically; the comparison is bit-exact
-    r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-I" + inc, "-I" + csrc, src, "-o", exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-DRIFE_FUSED_LEAN=%d" % lean, "-I" + inc, "-I" + csrc, src, "-o", exe],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-4000:]
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "EMU OK" in r.stdout, r.stdout[-4000:]
+    return [l for l in r.stdout.splitlines() if l.startswith("checksum")][0]
+
+
+def test_fused_kernels_host_emulation(tmp_path):
+    _build_and_run(tmp_path, 0)
+
+
+def test_lean_build_of_the_fused_kernels_is_bit_identical(tmp_path):
+    """RIFE_FUSED_LEAN=1 (integer lin_coeff, packed half conversions): same head tensors and frames, byte for byte."""
+    assert _build_and_run(tmp_path, 0) == _build_and_run(tmp_path, 1)
