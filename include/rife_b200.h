@@ -9,6 +9,7 @@
  *   rife_b200_create         RIFE::RIFE(gpuid, tta, tta_temporal, uhd,   src/rife.cpp:27-47, call site main.cpp:825
  *                                       num_threads, rife_v2, rife_v4)
  *   rife_b200_load           RIFE::load(modeldir)                        src/rife.cpp:127-379, call site main.cpp:827
+ *   rife_b200_load_w         RIFE::load(const std::wstring&)             src/rife.cpp:80-110 (the Windows build's overload)
  *   rife_b200_process        RIFE::process(in0, in1, timestep, out)      src/rife.cpp:381-405, call site main.cpp:360
  *   rife_b200_destroy        RIFE::~RIFE()                               src/rife.cpp:49-78
  * Additions for the stream / benchmark path (no reference counterpart; the reference re-uploads per call):
@@ -24,6 +25,7 @@
 #define RIFE_B200_H
 
 #include <stddef.h>
+#include <wchar.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -45,6 +47,8 @@ int rife_b200_create(rife_b200_t** handle, int gpuid, int tta_mode, int tta_temp
 
 /* reads flownet.{param,bin} (+ contextnet / fusionnet unless rife_v4), as the reference does */
 int rife_b200_load(rife_b200_t* handle, const char* modeldir);
+/* wide-character path (the reference's Windows overload); converted to UTF-8 */
+int rife_b200_load_w(rife_b200_t* handle, const wchar_t* modeldir);
 
 /* in0/in1/out: packed RGB u8, HWC, w*h*3 bytes each, caller-owned HOST memory.
  * timestep == 0 / 1 copies in0 / in1 to out (the reference rebinds the output Mat, src/rife.cpp:3206-3216). */
@@ -72,11 +76,28 @@ int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned ch
  * "plain_blocks" (bit k: IFBlock k's residual chain uses plain fp16 activations instead of split hi+lo; default 12),
  * "fast" (0/1 fused rife-v4.6 path), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path),
  * "combine" (0/1, default 1: concurrent rife_b200_process calls on one handle run as one lock-step batch),
- * "recompute_fm" (0-2, default 0: fused path rebuilds the full-resolution flow / mask planes instead of storing them) */
+ * "recompute_fm" (0-2, default 0: fused path rebuilds the full-resolution flow / mask planes instead of storing them),
+ * "cpu_crop_quirk" (0/1, default 0).  The output frame is the w x h crop of the padded result, as the reference's GPU path
+ *   produces it (src/rife_postproc.comp:42).  The reference's CPU path instead reads the first w*h floats of every padded
+ *   channel contiguously (src/rife.cpp:4375-4387), which shears the frame whenever w % 32 != 0; 1 reproduces that
+ *   byte for byte (used by the parity tests against the reference's -g -1 binary).  No difference when w % 32 == 0.
+ * "bgr" (0/1, default 0): frame bytes are B,G,R -- the reference's Windows build (src/rife_preproc.comp:13,53-56),
+ * "frame_cache" (0/1, default 0): input frames uploaded by rife_b200_process / _process_batch stay on the device and are
+ *   found again by host pointer in later calls (pair (k, k+1) then uploads only frame k+1).  The caller must not modify
+ *   or free-and-reuse a frame buffer it has handed in until rife_b200_forget_frames() or "frame_cache" = 0.
+ *   Within one call a frame shared by several pairs is always uploaded once. */
 int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
 /* reads back "precision", "lanes", "fast" (requested) and "fast_active" (1 when the fused rife-v4.6 path passed its
  * load-time self-check against the generic executor and is the one process() runs) */
 int rife_b200_get_option(rife_b200_t* handle, const char* key, int* value);
+
+/* Diagnostics: with option "ktime" = 1 the fused path records CUDA-event times of every stage of a lock-step batch (the
+ * stream is synchronised after each batch while it is on).  Text, one block per lane: "lane\t<i>", "batches\t<n>", then
+ * "<stage>\t<microseconds per batch>\t<kernel launches per batch>" per stage.  bench.py's per-stage breakdown. */
+int rife_b200_stage_report(rife_b200_t* handle, char* buf, size_t cap);
+
+/* drops every cached input frame (option "frame_cache") */
+int rife_b200_forget_frames(rife_b200_t* handle);
 
 /* packed-weights path for multi-GPU loading without re-reading the model directory on every rank */
 int rife_b200_weights_size(rife_b200_t* handle, size_t* bytes);                 /* after load() on rank 0 */
@@ -112,6 +133,14 @@ int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w
                             const float* weight, const float* bias, const float* res, float slope, float* out_tc,
                             float* out_ref);
 
+/* Diagnostics: the HBM-side kernels of the generic path (csrc/hbm_kernels.cu) on caller data (iters == 0: one launch, result
+ * copied back; used by tests/test_hbm_kernels_gpu.py against numpy restatements) or on device-resident synthetic data
+ * (iters > 0: `iters` launches on `cuda_stream`, nothing copied; used by tools/bench_hbm.py for GB/s and ncu captures).
+ * which: 0 preproc (c = orientations), 1 postproc (c = inputs), 2 flow_tta_avg (c = channels), 3 warp (c = channels),
+ * 4 temporal_merge_v2 (c = has_mask), 5 temporal_merge_v1; buffer layouts: see csrc/capi.cu. */
+int rife_b200_debug_hbm(int gpuid, void* cuda_stream, int which, int w, int h, int c, int iters, const void* in, const void* in2,
+                        void* out);
+
 /* Diagnostics (host only, no GPU): parses one network (<name>.param + <name>.bin, the reference's model format:
  * src/ncnn/src/net.cpp:1374-1590, modelbin.cpp:89-260) and reports its layer / blob / weight-value counts; on failure
  * returns RIFE_B200_ERR_MODEL with the loader's message in `err` (may be NULL). */
@@ -132,7 +161,8 @@ unsigned long long rife_b200_launch_count(void);
 unsigned long long rife_b200_h2d_bytes(void);
 unsigned long long rife_b200_d2h_bytes(void);
 
-/* last error message of the handle (thread-unsafe convenience for diagnostics); never NULL */
+/* last error message of the handle, copied into a buffer owned by the calling thread (valid until that thread's next call
+ * of this function); never NULL */
 const char* rife_b200_last_error(rife_b200_t* handle);
 
 void rife_b200_destroy(rife_b200_t* handle);

@@ -31,6 +31,9 @@ def lib():
     L.rife_b200_device_count.restype = ci
     L.rife_b200_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci, ci]
     L.rife_b200_load.argtypes = [vp, ctypes.c_char_p]
+    L.rife_b200_load_w.argtypes = [vp, ctypes.c_wchar_p]
+    L.rife_b200_forget_frames.argtypes = [vp]
+    L.rife_b200_stage_report.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
     L.rife_b200_process.argtypes = [vp, vp, vp, ci, ci, cf, vp]
     L.rife_b200_process_device.argtypes = [vp, vp, vp, ci, ci, cf, vp]
     L.rife_b200_process_batch.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ctypes.POINTER(cf), ctypes.POINTER(vp)]
@@ -46,6 +49,7 @@ def lib():
     L.rife_b200_selftest_conv.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, cf, vp, vp]
     L.rife_b200_debug_parse_model.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_char_p, ci]
     L.rife_b200_debug_pack_weights.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, ctypes.c_size_t]
+    L.rife_b200_debug_hbm.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.rife_b200_launch_count.restype = ctypes.c_ulonglong
     L.rife_b200_h2d_bytes.restype = ctypes.c_ulonglong
     L.rife_b200_d2h_bytes.restype = ctypes.c_ulonglong
@@ -57,10 +61,10 @@ def lib():
     return L
 
 
-EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_process", "rife_b200_process_device",
+EXPORTS = ["rife_b200_device_count", "rife_b200_create", "rife_b200_load", "rife_b200_load_w", "rife_b200_forget_frames", "rife_b200_stage_report", "rife_b200_process", "rife_b200_process_device",
            "rife_b200_process_batch", "rife_b200_process_batch_device", "rife_b200_set_option", "rife_b200_get_option", "rife_b200_weights_size", "rife_b200_weights_export",
            "rife_b200_load_packed", "rife_b200_selftest_conv", "rife_b200_set_stream", "rife_b200_bench_conv", "rife_b200_bench_conv_batched",
-           "rife_b200_debug_conv_timeline", "rife_b200_debug_pack_weights", "rife_b200_debug_parse_model",
+           "rife_b200_debug_conv_timeline", "rife_b200_debug_hbm", "rife_b200_debug_pack_weights", "rife_b200_debug_parse_model",
            "rife_b200_launch_count", "rife_b200_h2d_bytes", "rife_b200_d2h_bytes", "rife_b200_last_error", "rife_b200_destroy"]
 
 
@@ -98,6 +102,28 @@ class RIFE:
     def load(self, modeldir):
         self._check(self._lib.rife_b200_load(self._h, os.fsencode(modeldir)), "load(%s)" % modeldir)
         return 0
+
+    def load_w(self, modeldir):
+        self._check(self._lib.rife_b200_load_w(self._h, str(modeldir)), "load_w(%s)" % modeldir)
+        return 0
+
+    def stage_report(self):
+        """{lane: {"batches": n, "stages": [(name, us_per_batch, launches_per_batch), ...]}} (option "ktime" = 1)."""
+        buf = ctypes.create_string_buffer(16384)
+        self._check(self._lib.rife_b200_stage_report(self._h, buf, len(buf)), "stage_report")
+        out, cur = {}, None
+        for line in buf.value.decode().splitlines():
+            f = line.split("\t")
+            if f[0] == "lane":
+                cur = out.setdefault(int(f[1]), {"batches": 0, "stages": []})
+            elif f[0] == "batches" and cur is not None:
+                cur["batches"] = int(f[1])
+            elif cur is not None and len(f) == 3:
+                cur["stages"].append((f[0], float(f[1]), int(f[2])))
+        return out
+
+    def forget_frames(self):
+        self._check(self._lib.rife_b200_forget_frames(self._h), "forget_frames")
 
     def set_option(self, key, value):
         self._check(self._lib.rife_b200_set_option(self._h, key.encode(), int(value)), "set_option(%s)" % key)
@@ -173,6 +199,18 @@ def debug_conv_timeline(cin, cout, h, w, split=True, max_ctas=148, gpuid=0, batc
     if rc != 0:
         raise RifeError("debug_conv_timeline failed: %d" % rc)
     return buf
+
+
+HBM_KERNELS = {"preproc": 0, "postproc": 1, "flow_tta_avg": 2, "warp": 3, "temporal_merge_v2": 4, "temporal_merge_v1": 5}
+
+
+def debug_hbm(which, w, h, c, a=None, b=None, out=None, iters=0, cuda_stream_ptr=None, gpuid=0):
+    """One of the HBM-side kernels on host arrays (iters = 0) or `iters` launches on synthetic device data (timing)."""
+    rc = lib().rife_b200_debug_hbm(gpuid, ctypes.c_void_p(cuda_stream_ptr or 0), HBM_KERNELS[which], int(w), int(h), int(c), int(iters),
+                                   None if a is None else a.ctypes.data, None if b is None else b.ctypes.data, None if out is None else out.ctypes.data)
+    if rc != 0:
+        raise RifeError("debug_hbm(%s) failed: %d" % (which, rc))
+    return out
 
 
 def launch_count():

@@ -121,7 +121,7 @@ int rife_b200_weights_size(rife_b200_t* h, size_t* bytes) {
 int rife_b200_weights_export(rife_b200_t* h, void* dst, size_t bytes) {
     GUARD_BEGIN
     if (!h || !dst) return RIFE_B200_ERR_ARG;
-    const std::string& p = h->eng->packed();
+    const std::string p = h->eng->packed();
     if (p.empty()) return RIFE_B200_ERR_STATE;
     if (bytes < p.size()) return RIFE_B200_ERR_ARG;
     memcpy(dst, p.data(), p.size());
@@ -140,7 +140,47 @@ unsigned long long rife_b200_launch_count(void) { return rife::g_launch_count; }
 unsigned long long rife_b200_h2d_bytes(void) { return rife::g_h2d_bytes; }
 unsigned long long rife_b200_d2h_bytes(void) { return rife::g_d2h_bytes; }
 
-const char* rife_b200_last_error(rife_b200_t* h) { return h ? h->eng->last_error.c_str() : "null handle"; }
+// the message is copied into a per-thread buffer: several threads may use (and fail on) one handle concurrently
+const char* rife_b200_last_error(rife_b200_t* h) {
+    static thread_local std::string buf;
+    if (!h) return "null handle";
+    try { buf = h->eng->last_error(); } catch (...) { return "out of memory"; }
+    return buf.c_str();
+}
+
+int rife_b200_stage_report(rife_b200_t* h, char* buf, size_t cap) {
+    GUARD_BEGIN
+    if (!h || !buf || cap == 0) return RIFE_B200_ERR_ARG;
+    const std::string r = h->eng->stage_report();
+    snprintf(buf, cap, "%s", r.c_str());
+    return RIFE_B200_OK;
+    GUARD_END
+}
+
+int rife_b200_forget_frames(rife_b200_t* h) {
+    GUARD_BEGIN
+    if (!h) return RIFE_B200_ERR_ARG;
+    h->eng->forget_frames();
+    return RIFE_B200_OK;
+    GUARD_END
+}
+
+// RIFE::load(const std::wstring&) of the reference's Windows build (src/rife.cpp:80-110): the path is converted to UTF-8
+int rife_b200_load_w(rife_b200_t* h, const wchar_t* modeldir) {
+    GUARD_BEGIN
+    if (!h || !modeldir) return RIFE_B200_ERR_ARG;
+    std::string u8;
+    for (const wchar_t* p = modeldir; *p; p++) {
+        uint32_t c = (uint32_t)*p;
+        if (sizeof(wchar_t) == 2 && c >= 0xD800 && c <= 0xDBFF && p[1] >= 0xDC00 && p[1] <= 0xDFFF) { c = 0x10000 + ((c - 0xD800) << 10) + ((uint32_t)p[1] - 0xDC00); p++; }
+        if (c < 0x80) u8 += (char)c;
+        else if (c < 0x800) { u8 += (char)(0xC0 | (c >> 6)); u8 += (char)(0x80 | (c & 0x3F)); }
+        else if (c < 0x10000) { u8 += (char)(0xE0 | (c >> 12)); u8 += (char)(0x80 | ((c >> 6) & 0x3F)); u8 += (char)(0x80 | (c & 0x3F)); }
+        else { u8 += (char)(0xF0 | (c >> 18)); u8 += (char)(0x80 | ((c >> 12) & 0x3F)); u8 += (char)(0x80 | ((c >> 6) & 0x3F)); u8 += (char)(0x80 | (c & 0x3F)); }
+    }
+    return map_err(h->eng->load(u8));
+    GUARD_END
+}
 
 void rife_b200_destroy(rife_b200_t* h) {
     if (!h) return;
@@ -436,5 +476,91 @@ extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int ci
         if (r) return RIFE_B200_ERR_INTERNAL;
     }
     return cudaGetLastError() == cudaSuccess ? RIFE_B200_OK : RIFE_B200_ERR_DEVICE;
+    GUARD_END
+}
+
+// ---- diagnostics of the HBM-side kernels (hbm_kernels.cu) ---------------------------------------------------------------
+// which: 0 preproc (c = orientations 1 | 8; in = u8 [h][w][3]; out = float [c][3][hp][wp], orientations >= 4 transposed)
+//        1 postproc (c = inputs 1 | 2 | 8 | 16; in = float [c][3][hp*wp], input i in orientation i & 7; out = u8 [h][w][3])
+//        2 flow_tta_avg (c = channels 2 | 4 | 5; in = 8 blobs of c planes of h x w (blobs 4-7 transposed); out = same, averaged)
+//        3 warp (in = float [c][h][w], in2 = flow [2][h][w]; out = float [c][h][w])
+//        4 temporal_merge_v2 (c = has_mask; in = f, in2 = fr, 4 + c planes of w*h; out = f' followed by fr')
+//        5 temporal_merge_v1 (2 planes)
+// iters > 0: timing mode -- synthetic device-resident data, the kernel is launched `iters` times on `cuda_stream`, nothing is
+// copied (in / in2 / out may be NULL).  iters == 0: test mode -- one launch on the host data, result copied back.
+extern "C" int rife_b200_debug_hbm(int gpuid, void* cuda_stream, int which, int w, int h, int c, int iters, const void* in, const void* in2, void* out) {
+    GUARD_BEGIN
+    using namespace rife;
+    if (w <= 0 || h <= 0 || c <= 0 || which < 0 || which > 5 || iters < 0) return RIFE_B200_ERR_ARG;
+    if (iters == 0 && (!in || !out)) return RIFE_B200_ERR_ARG;
+    if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
+    const size_t plane = (size_t)wp * hp, n = (size_t)w * h;
+    size_t in_b = 0, in2_b = 0, out_b = 0;
+    switch (which) {
+        case 0: in_b = n * 3; out_b = (size_t)c * 3 * plane * 4; break;
+        case 1: in_b = (size_t)c * 3 * plane * 4; out_b = n * 3; break;
+        case 2: in_b = out_b = (size_t)8 * c * n * 4; break;
+        case 3: in_b = out_b = (size_t)c * n * 4; in2_b = 2 * n * 4; break;
+        case 4: in_b = in2_b = (size_t)(4 + (c ? 1 : 0)) * n * 4; out_b = 2 * in_b; break;
+        default: in_b = in2_b = 2 * n * 4; out_b = 2 * in_b; break;
+    }
+    // timing mode keeps its buffers between calls of the same shape (bench loops); test mode allocates and frees
+    struct Cache { int which = -1, w = 0, h = 0, c = 0; void *a = 0, *b = 0, *o = 0; };
+    static Cache cache;
+    void *d_in = 0, *d_in2 = 0, *d_out = 0;
+    const bool timing = iters > 0;
+    if (timing && cache.which == which && cache.w == w && cache.h == h && cache.c == c) { d_in = cache.a; d_in2 = cache.b; d_out = cache.o; }
+    else {
+        if (timing) { cudaFree(cache.a); cudaFree(cache.b); cudaFree(cache.o); cache = Cache(); }
+        if (cudaMalloc(&d_in, in_b) != cudaSuccess || (in2_b && cudaMalloc(&d_in2, in2_b) != cudaSuccess) || cudaMalloc(&d_out, out_b) != cudaSuccess) {
+            cudaFree(d_in); cudaFree(d_in2); cudaFree(d_out);
+            return RIFE_B200_ERR_DEVICE;
+        }
+        if (timing) {
+            cudaMemset(d_in, which == 0 ? 0x5a : 0, in_b);  // flows of zero: the warp gathers its own pixel (best-case locality is what a smooth flow gives)
+            if (d_in2) cudaMemset(d_in2, 0, in2_b);
+            cache.which = which; cache.w = w; cache.h = h; cache.c = c; cache.a = d_in; cache.b = d_in2; cache.o = d_out;
+        } else {
+            cudaMemcpy(d_in, in, in_b, cudaMemcpyHostToDevice);
+            if (d_in2) cudaMemcpy(d_in2, in2, in2_b, cudaMemcpyHostToDevice);
+        }
+    }
+    const int reps = timing ? iters : 1;
+    for (int it = 0; it < reps; it++) {
+        switch (which) {
+            case 0: launch_preproc((const uint8_t*)d_in, w, h, (float*)d_out, wp, hp, c, 0, st); break;
+            case 1: {
+                const float* ins[16];
+                for (int i = 0; i < c && i < 16; i++) ins[i] = (const float*)d_in + (size_t)i * 3 * plane;
+                launch_postproc(ins, c, wp, hp, (uint8_t*)d_out, w, h, 0, 0, st);
+                break;
+            }
+            case 2: {
+                float* f8[8];
+                if (!timing || it == 0) cudaMemcpyAsync(d_out, d_in, in_b, cudaMemcpyDeviceToDevice, st);
+                for (int i = 0; i < 8; i++) f8[i] = (float*)d_out + (size_t)i * c * n;
+                launch_flow_tta_avg(f8, c, w, h, st);
+                break;
+            }
+            case 3: launch_warp((const float*)d_in, (const float*)d_in2, (float*)d_out, c, h, w, st); break;
+            case 4:
+            case 5: {
+                if (!timing || it == 0) {
+                    cudaMemcpyAsync(d_out, d_in, in_b, cudaMemcpyDeviceToDevice, st);
+                    cudaMemcpyAsync((char*)d_out + in_b, d_in2, in_b, cudaMemcpyDeviceToDevice, st);
+                }
+                if (which == 4) launch_temporal_merge_v2((float*)d_out, (float*)((char*)d_out + in_b), n, c ? 1 : 0, st);
+                else launch_temporal_merge_v1((float*)d_out, (float*)((char*)d_out + in_b), n, st);
+                break;
+            }
+        }
+    }
+    if (timing) return cudaGetLastError() == cudaSuccess ? RIFE_B200_OK : RIFE_B200_ERR_DEVICE;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_b, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_in2); cudaFree(d_out);
+    return e == cudaSuccess ? RIFE_B200_OK : RIFE_B200_ERR_DEVICE;
     GUARD_END
 }

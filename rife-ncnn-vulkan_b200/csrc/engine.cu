@@ -37,7 +37,9 @@ void Lane::release() {
     delete fast;
     fast = nullptr;
     for (auto& r : run) { delete r; r = nullptr; }
-    for (int i = 0; i < 8; i++) { pad0[i].release(); pad1[i].release(); tmp[i].release(); }
+    pad0.release();
+    pad1.release();
+    for (int i = 0; i < 8; i++) tmp[i].release();
     for (int i = 0; i < 2; i++) { ts[i].release(); tsr[i].release(); for (auto& c : ctx[i]) c.release(); }
     for (auto& a : flow) for (auto& b : a) b.release();
     for (auto& a : flowr) for (auto& b : a) b.release();
@@ -53,7 +55,8 @@ Engine::~Engine() {
     cudaDeviceSynchronize();
     // borrowers first, the weight-owning lane 0 last
     for (size_t i = lanes_.size(); i-- > 0;) { lanes_[i]->release(); delete lanes_[i]; }
-    for (auto& b : u8_) b.release();
+    for (auto& b : out_u8_) b.release();
+    for (auto& f : frames_) { f.buf.release(); if (f.read_done) cudaEventDestroy(f.read_done); }
     for (int i = 0; i < kSlots; i++) {
         if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
         if (ev_comp_[i]) cudaEventDestroy(ev_comp_[i]);
@@ -65,8 +68,8 @@ Engine::~Engine() {
 
 int Engine::init() {
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || gpuid_ < 0 || gpuid_ >= n) { last_error = "no such CUDA device"; return -2; }
-    if (cudaSetDevice(gpuid_) != cudaSuccess) { last_error = "cudaSetDevice failed"; return -2; }
+    if (cudaGetDeviceCount(&n) != cudaSuccess || gpuid_ < 0 || gpuid_ >= n) { set_error("no such CUDA device"); return -2; }
+    if (cudaSetDevice(gpuid_) != cudaSuccess) { set_error("cudaSetDevice failed"); return -2; }
     for (auto& s : st_copy_) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     for (int i = 0; i < kSlots; i++) {
         cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming);
@@ -84,7 +87,7 @@ int Engine::make_lanes(int n) {
     while ((int)lanes_.size() > n) { lanes_.back()->release(); delete lanes_.back(); lanes_.pop_back(); }
     while ((int)lanes_.size() < n) {
         Lane* L = new Lane();
-        if (cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking) != cudaSuccess) { delete L; last_error = "stream creation failed"; return -2; }
+        if (cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking) != cudaSuccess) { delete L; set_error("stream creation failed"); return -2; }
         cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming);
         if (!lanes_.empty())
             for (int i = 0; i < 3; i++)
@@ -117,7 +120,7 @@ int Engine::load(const std::string& modeldir) {
     for (int i = 0; i < nn; i++) {
         std::string p, b;
         if (!read_file(modeldir + "/" + kNetNames[i] + ".param", p) || !read_file(modeldir + "/" + kNetNames[i] + ".bin", b)) {
-            last_error = "cannot read " + modeldir + "/" + kNetNames[i] + ".{param,bin}";
+            set_error("cannot read " + modeldir + "/" + kNetNames[i] + ".{param,bin}");
             return -3;
         }
         uint64_t pl = p.size(), bl = b.size();
@@ -129,48 +132,80 @@ int Engine::load(const std::string& modeldir) {
     return load_packed(blob.data(), blob.size());
 }
 
+// Transactional: the new model is parsed and uploaded into temporaries; the engine's state changes only after every
+// network loaded, so a failing (re)load leaves a previously loaded engine exactly as it was.
 int Engine::load_packed(const void* data, size_t bytes) {
     std::lock_guard<std::mutex> lk(mu_);
     cudaSetDevice(gpuid_);
     const char* p = (const char*)data;
-    if (bytes < 12 || memcmp(p, "RIFEB200", 8)) { last_error = "bad packed model"; return -3; }
+    if (bytes < 12 || memcmp(p, "RIFEB200", 8)) { set_error("bad packed model"); return -3; }
     uint32_t nn;
     memcpy(&nn, p + 8, 4);
-    if (nn != (uint32_t)(v4_ ? 1 : 3)) { last_error = "packed model does not match the model family flags"; return -3; }
+    if (nn != (uint32_t)(v4_ ? 1 : 3)) { set_error("packed model does not match the model family flags"); return -3; }
     size_t pos = 12;
+    std::unique_ptr<Net> nets[3];
+    std::unique_ptr<NetRunner> runs[3];
+    int num_sms = 148;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, gpuid_) == cudaSuccess) num_sms = prop.multiProcessorCount;
+    }
     for (uint32_t i = 0; i < nn; i++) {
         uint64_t pl, bl;
-        if (pos + 16 > bytes) { last_error = "truncated packed model"; return -3; }
+        if (bytes - pos < 16) { set_error("truncated packed model"); return -3; }
         memcpy(&pl, p + pos, 8);
         memcpy(&bl, p + pos + 8, 8);
         pos += 16;
-        if (pos + pl + bl > bytes) { last_error = "truncated packed model"; return -3; }
+        if (pl > bytes - pos || bl > bytes - pos - pl) { set_error("truncated packed model"); return -3; }  // no u64 wrap-around
         std::string ptxt(p + pos, (size_t)pl), bbin(p + pos + pl, (size_t)bl);
-        pos += pl + bl;
+        pos += (size_t)pl + (size_t)bl;
         std::string err;
-        nets_[i] = Net();
-        if (parse_net(ptxt, bbin, kNetNames[i], nets_[i], err)) { last_error = err; return -3; }
-        cudaDeviceSynchronize();
-        for (size_t li = lanes_.size(); li-- > 0;) { delete lanes_[li]->run[i]; lanes_[li]->run[i] = nullptr; }
-        NetRunner* r0 = new NetRunner();
-        lanes_[0]->run[i] = r0;
-        r0->tc_mode = precision_;
-        {
-            cudaDeviceProp prop;
-            if (cudaGetDeviceProperties(&prop, gpuid_) == cudaSuccess) r0->num_sms = prop.multiProcessorCount;
-        }
-        if (r0->init(&nets_[i], err)) { last_error = err; return -3; }
-        for (size_t li = 1; li < lanes_.size(); li++) { lanes_[li]->run[i] = new NetRunner(); lanes_[li]->run[i]->share_from(*r0); }
+        nets[i].reset(new Net());
+        if (parse_net(ptxt, bbin, kNetNames[i], *nets[i], err)) { set_error(err); return -3; }
+        runs[i].reset(new NetRunner());
+        runs[i]->tc_mode = precision_;
+        runs[i]->num_sms = num_sms;
+        if (runs[i]->init(nets[i].get(), err)) { set_error(err); cudaGetLastError(); return -3; }
+    }
+    // commit
+    cudaDeviceSynchronize();
+    loaded_ = false;
+    fast_ok_ = false;
+    publish();
+    for (Lane* L : lanes_) { delete L->fast; L->fast = nullptr; }
+    for (size_t li = lanes_.size(); li-- > 0;)  // borrowers first
+        for (int i = 0; i < 3; i++) { delete lanes_[li]->run[i]; lanes_[li]->run[i] = nullptr; }
+    for (uint32_t i = 0; i < 3; i++) {
+        nets_[i] = std::move(nets[i]);
+        if (i >= nn) continue;
+        lanes_[0]->run[i] = runs[i].release();
+        for (size_t li = 1; li < lanes_.size(); li++) { lanes_[li]->run[i] = new NetRunner(); lanes_[li]->run[i]->share_from(*lanes_[0]->run[i]); }
     }
     packed_.assign(p, bytes);
     loaded_ = true;
-    if ((int)lanes_.size() != nlanes_) { int r = make_lanes(nlanes_); if (r) return r; }
+    if ((int)lanes_.size() != nlanes_) { int r = make_lanes(nlanes_); if (r) { loaded_ = false; publish(); return r; } }
     setup_fast();
+    publish();
     return 0;
+}
+
+void Engine::publish() {
+    snap_combine_.store(combine_ && loaded_ ? 1 : 0, std::memory_order_relaxed);
+    snap_fast_.store(loaded_ && fast_usable() ? 1 : 0, std::memory_order_relaxed);
+    snap_batch_.store(batch_, std::memory_order_relaxed);
+    snap_lanes_.store((int)lanes_.size(), std::memory_order_release);
+}
+
+void Engine::sync_all() {
+    for (auto& s : st_copy_) if (s) cudaStreamSynchronize(s);
+    for (Lane* L : lanes_) if (L->st) cudaStreamSynchronize(L->st);
+    if (use_user_stream_) cudaStreamSynchronize(user_stream_);
+    cudaGetLastError();
 }
 
 int Engine::set_option(const std::string& key, int value) {
     std::lock_guard<std::mutex> lk(mu_);
+    struct Pub { Engine* e; ~Pub() { e->publish(); } } pub{this};
     if (key == "precision") {  // 0 exact fp32, 1 tensor cores + split-fp16 activations, 2 tensor cores + plain fp16 activations
         precision_ = value;
         cudaDeviceSynchronize();
@@ -197,12 +232,46 @@ int Engine::set_option(const std::string& key, int value) {
         for (Lane* L : lanes_) if (L->fast) L->fast->set_recompute(recompute_fm_);
         return 0;
     }
+    if (key == "cpu_crop_quirk") {  // 1: the output is the reference CPU path's contiguous read of the padded planes (rife.cpp:4375-4387)
+        cpu_crop_quirk_ = value != 0;
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_crop_quirk(cpu_crop_quirk_);
+        return 0;
+    }
+    if (key == "bgr") {  // frames are B,G,R in memory (the reference's Windows build)
+        bgr_ = value != 0;
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_bgr(bgr_);
+        for (auto& f : frames_) f.host = nullptr;
+        return 0;
+    }
+    if (key == "frame_cache") {  // 1: uploaded input frames stay on the device across calls, found again by host pointer
+        frame_cache_ = value != 0;
+        if (!frame_cache_) for (auto& f : frames_) f.host = nullptr;
+        return 0;
+    }
+    if (key == "ktime") {  // per-stage event times on the fused path (stage_report); lanes no longer overlap while it is on
+        cudaDeviceSynchronize();
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_ktime(value);
+        return 0;
+    }
     if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
     if (key == "combine") { combine_ = value != 0; return 0; }
     if (key == "fuse") { cudaDeviceSynchronize(); for (Lane* L : lanes_) for (auto& r : L->run) if (r) { r->fuse = value != 0; r->clear_plans(); } return 0; }
-    last_error = "unknown option " + key;
+    set_error("unknown option " + key);
     return -1;
+}
+
+std::string Engine::stage_report() {
+    std::lock_guard<std::mutex> lk(mu_);
+    std::string r;
+    for (size_t i = 0; i < lanes_.size(); i++)
+        if (lanes_[i]->fast) r += "lane\t" + std::to_string(i) + "\n" + lanes_[i]->fast->stage_report();
+    return r;
+}
+
+void Engine::forget_frames() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& f : frames_) f.host = nullptr;
 }
 
 int Engine::get_option(const std::string& key, int* value) {
@@ -214,10 +283,14 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "plain_blocks") *value = plain_mask_;
     else if (key == "recompute_fm") *value = recompute_fm_;
     else if (key == "combine") *value = combine_;
+    else if (key == "cpu_crop_quirk") *value = cpu_crop_quirk_;
+    else if (key == "bgr") *value = bgr_;
+    else if (key == "frame_cache") *value = frame_cache_;
+    else if (key == "frame_cache_hits") *value = (int)frame_hits_;
     else if (key == "combined_batches") *value = (int)combiner_.batches();
     else if (key == "combined_requests") *value = (int)combiner_.requests();
-    else if (key == "fast_active") *value = fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1;
-    else { last_error = "unknown option " + key; return -1; }
+    else if (key == "fast_active") *value = fast_usable();
+    else { set_error("unknown option " + key); return -1; }
     return 0;
 }
 
@@ -232,7 +305,9 @@ void Engine::setup_fast() {
     for (Lane* L : lanes_) {
         L->fast = new V46Runner();
         L->fast->set_recompute(recompute_fm_);
-        if (L->fast->init(&nets_[0], lanes_[0]->run[0], err)) {
+        L->fast->set_crop_quirk(cpu_crop_quirk_);
+        L->fast->set_bgr(bgr_);
+        if (L->fast->init(nets_[0].get(), lanes_[0]->run[0], err)) {
             for (Lane* L2 : lanes_) { delete L2->fast; L2->fast = nullptr; }
             return;
         }
@@ -269,6 +344,7 @@ void Engine::setup_fast() {
         size_t ne = 0;
         for (size_t i = 0; i < n; i++) { int d = abs((int)o0[i] - (int)o1[i]); maxd = std::max(maxd, d); ne += d != 0; }
         ok = maxd <= 1 && ne * 200 < n;  // identical up to fp32 rounding: at most a few 1-LSB flips
+        if (getenv("RIFE_B200_VERBOSE")) fprintf(stderr, "[rife_b200] fused-path self-check (%s layout): max diff %d, %zu of %zu bytes differ -> %s\n", L.fast->is_v4() ? "rife-v4" : "rife-v4.6", maxd, ne, n, ok ? "enabled" : "disabled");
     } while (0);
     cudaGetLastError();
     for (Lane* LL : lanes_) { LL->run[0]->tc_mode = saved_mode; LL->run[0]->clear_plans(); }
@@ -287,24 +363,25 @@ Tensor Engine::keep(const Tensor& t, DevBuf& b, cudaStream_t st) {
 }
 
 // pairs per lock-step batch: enough images to fill the machine in the coarse IFBlocks (about one 4K frame of pixels)
-int Engine::batch_for(int w, int h) const {
-    if (!(fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1)) return 1;
-    if (batch_ > 0) return batch_;
+static int batch_rule(bool fast, int batch_opt, int w, int h) {
+    if (!fast) return 1;
+    if (batch_opt > 0) return batch_opt;
     const size_t px = (size_t)((w + 31) / 32 * 32) * ((h + 31) / 32 * 32);
     size_t b = (size_t)2 * 3840 * 2176 / (px ? px : 1);  // measured: 8 pairs at 1080p, 2 at 4K (profiles/README.md)
     if (b < 1) b = 1;
     if (b > V46_MAX_BATCH) b = V46_MAX_BATCH;
     return (int)b;
 }
+int Engine::batch_for(int w, int h) const { return batch_rule(fast_usable(), batch_, w, h); }
 
 // n pairs on one lane: one lock-step batch on the fused path, otherwise pair by pair
 int Engine::run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st) {
-    if (n > 1 && fast_ok_ && use_fast_ && L.fast && v4_ && !tta_ && !ttat_ && precision_ == 1) {
+    if (n > 1 && fast_usable() && L.fast) {
         std::string err;
         int r = L.fast->run_batch(n, d_in0, d_in1, w, h, ts, d_out, st, err);
-        if (r) { last_error = err; return -5; }
+        if (r) { set_error(err); return -5; }
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
+        if (e != cudaSuccess) { set_error(std::string("kernel launch failure: ") + cudaGetErrorString(e)); return -2; }
         return 0;
     }
     for (int i = 0; i < n; i++) {
@@ -318,13 +395,17 @@ int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, f
     const uint8_t* a[1] = {in0};
     const uint8_t* b[1] = {in1};
     uint8_t* o[1] = {out};
-    if (!in0 || !in1 || !out) { last_error = "bad argument"; return -1; }
+    if (!in0 || !in1 || !out) { set_error("bad argument"); return -1; }
     // The reference's CLI calls process() from several proc threads on one object (src/main.cpp:346-366): requests that
     // arrive while another is being served are executed together as one lock-step batch instead of one after the other.
-    if (combine_ && loaded_ && w > 0 && h > 0 && batch_for(w, h) > 1) {
-        HostReq r = {in0, in1, w, h, t, out};
-        int cap = batch_for(w, h) * (int)lanes_.size();
-        return combiner_.submit(&r, cap, [this](HostReq** rq, int n) { return run_combined(rq, n); });
+    // Decided from a lock-free snapshot: the leader of a running batch holds mu_, followers must still be able to queue.
+    if (snap_combine_.load(std::memory_order_relaxed) && w > 0 && h > 0) {
+        const int nl = snap_lanes_.load(std::memory_order_acquire);
+        const int B = batch_rule(snap_fast_.load(std::memory_order_relaxed) != 0, snap_batch_.load(std::memory_order_relaxed), w, h);
+        if (B > 1) {
+            HostReq r = {in0, in1, w, h, t, out};
+            return combiner_.submit(&r, B * nl, [this](HostReq** rq, int n) { return run_combined(rq, n); });
+        }
     }
     return process_batch(1, a, b, w, h, &t, o);
 }
@@ -352,7 +433,7 @@ int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, in
     const uint8_t* a[1] = {d_in0};
     const uint8_t* b[1] = {d_in1};
     uint8_t* o[1] = {d_out};
-    if (!d_in0 || !d_in1 || !d_out) { last_error = "bad argument"; return -1; }
+    if (!d_in0 || !d_in1 || !d_out) { set_error("bad argument"); return -1; }
     return process_batch_device(1, a, b, w, h, &t, o);
 }
 
@@ -360,10 +441,12 @@ int Engine::process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, in
 // round-robin to the lanes; when the caller supplied a stream (set_stream) every lane first waits for that stream and
 // the stream finally waits for every lane, so events the caller records on it bracket all of the work.
 int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out) {
-    if (n < 0 || !d_in0 || !d_in1 || !d_out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
-    if (!loaded_) { last_error = "process before load"; return -4; }
+    if (n < 0 || !d_in0 || !d_in1 || !d_out || !ts || w <= 0 || h <= 0) { set_error("bad argument"); return -1; }
+    for (int i = 0; i < n; i++)  // validate everything before anything is queued
+        if (!d_in0[i] || !d_in1[i] || !d_out[i]) { set_error("null frame pointer"); return -1; }
     size_t nb = (size_t)w * h * 3;
     std::lock_guard<std::mutex> lk(mu_);
+    if (!loaded_) { set_error("process before load"); return -4; }
     cudaSetDevice(gpuid_);
     const int nl = (int)lanes_.size();
     const int B = batch_for(w, h);
@@ -382,7 +465,6 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
     if (per < 1) per = 1;
     for (int i = 0; i <= n; i++) {
         if (i < n) {
-            if (!d_in0[i] || !d_in1[i] || !d_out[i]) { last_error = "null frame pointer"; return -1; }
             if (ts[i] == 0.f || ts[i] == 1.f) {  // rife.cpp:3206-3216: the output is an input
                 cudaMemcpyAsync(d_out[i], ts[i] == 0.f ? d_in0[i] : d_in1[i], nb, cudaMemcpyDeviceToDevice, lanes_[chunk % nl]->st);
                 continue;
@@ -393,7 +475,7 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
         if (cn == per || (i == n && cn > 0)) {
             Lane& L = *lanes_[chunk % nl];
             int r = run_chunk(L, cn, c0, c1, w, h, ct, co, L.st);
-            if (r) return r;
+            if (r) { sync_all(); return r; }  // nothing of this call may still be running when the caller sees the error
             cn = 0;
             chunk++;
         }
@@ -406,18 +488,47 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
     cudaError_t e = cudaSuccess;
     for (int l = 0; l < nl; l++) { cudaError_t e2 = cudaStreamSynchronize(lanes_[l]->st); if (e2 != cudaSuccess) e = e2; }
     if (use_user_stream_) { cudaError_t e2 = cudaStreamSynchronize(user_stream_); if (e2 != cudaSuccess) e = e2; }
-    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+    if (e != cudaSuccess) { set_error(std::string("CUDA failure: ") + cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
-// Host frames, pipelined by chunk: slot s = chunk mod (2 * lanes) owns 3 device frame buffers per batch position; H2D
-// runs on one copy stream, compute on lane chunk mod lanes, D2H on the other copy stream, chained with events (pinned
-// host memory makes the copies truly asynchronous; pageable memory still works, the driver then stages synchronously).
+// Device copy of the host frame `host`: an entry that already holds it (same pointer and size; uploaded earlier in this
+// call, or in an earlier call when option "frame_cache" is on), else the least recently used entry that the chunk being
+// assembled (`cur`, `ncur`) does not use.  An evicted entry may still be read by a chunk in flight: the caller orders the new
+// upload behind its read_done event.  *hit tells the caller whether an upload is needed.
+Engine::FrameEntry* Engine::frame_lookup(const uint8_t* host, size_t nb, FrameEntry* const* cur, int ncur, bool* hit) {
+    const size_t kMaxFrames = 4 * (size_t)V46_MAX_BATCH * 2 + 2;  // ~4 chunks of 8 pairs with all-distinct frames
+    if (frames_.capacity() < kMaxFrames) frames_.reserve(kMaxFrames);  // entries are referenced by pointer: never reallocate
+    FrameEntry* lru = nullptr;
+    for (auto& f : frames_) {
+        if (f.host == host && f.nb == nb) { *hit = true; f.stamp = ++frame_clock_; return &f; }
+        bool in_cur = false;
+        for (int u = 0; u < ncur; u++) in_cur = in_cur || cur[u] == &f;
+        if (!in_cur && (!lru || f.stamp < lru->stamp)) lru = &f;
+    }
+    *hit = false;
+    if (frames_.size() < kMaxFrames) {
+        frames_.emplace_back();
+        lru = &frames_.back();
+        if (cudaEventCreateWithFlags(&lru->read_done, cudaEventDisableTiming) != cudaSuccess) { frames_.pop_back(); return nullptr; }
+    }
+    if (!lru) return nullptr;
+    lru->host = host;
+    lru->nb = nb;
+    lru->stamp = ++frame_clock_;
+    return lru;
+}
+
+// Host frames, pipelined by chunk: H2D runs on one copy stream, compute on lane chunk mod lanes, D2H on the other copy
+// stream, chained with events (pinned host memory makes the copies truly asynchronous; pageable memory still works, the
+// driver then stages synchronously).  Input frames live in the frame table (frame_lookup); outputs in per-slot buffers.
 int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out) {
-    if (n < 0 || !in0 || !in1 || !out || !ts || w <= 0 || h <= 0) { last_error = "bad argument"; return -1; }
-    if (!loaded_) { last_error = "process before load"; return -4; }
+    if (n < 0 || !in0 || !in1 || !out || !ts || w <= 0 || h <= 0) { set_error("bad argument"); return -1; }
+    for (int i = 0; i < n; i++)  // validate everything before anything is queued
+        if (!in0[i] || !in1[i] || !out[i]) { set_error("null frame pointer"); return -1; }
     size_t nb = (size_t)w * h * 3;
     std::lock_guard<std::mutex> lk(mu_);
+    if (!loaded_) { set_error("process before load"); return -4; }
     cudaSetDevice(gpuid_);
     const int nl = (int)lanes_.size();
     const int nslots = 2 * nl <= kSlots ? 2 * nl : kSlots;
@@ -425,54 +536,46 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     int per = B;
     if (n < per * nl) per = (n + nl - 1) / nl;
     if (per < 1) per = 1;
-    if (u8_.size() < (size_t)kSlots * 3 * V46_MAX_BATCH) u8_.resize((size_t)kSlots * 3 * V46_MAX_BATCH);
-    auto buf = [&](int slot, int pos, int which) -> DevBuf& { return u8_[((size_t)slot * V46_MAX_BATCH + pos) * 3 + which]; };
+    if (out_u8_.size() < (size_t)kSlots * V46_MAX_BATCH) out_u8_.resize((size_t)kSlots * V46_MAX_BATCH);
     std::vector<int> used(nslots, 0);
     const uint8_t* c0[V46_MAX_BATCH];
     const uint8_t* c1[V46_MAX_BATCH];
     uint8_t* co[V46_MAX_BATCH];
     uint8_t* ho[V46_MAX_BATCH];
     float ct[V46_MAX_BATCH];
-    const uint8_t* up_host[2 * V46_MAX_BATCH];
-    const uint8_t* up_dev[2 * V46_MAX_BATCH];
-    int nup = 0;
+    FrameEntry* fe[2 * V46_MAX_BATCH];
+    int nfe = 0;
     int cn = 0, chunk = 0;
-    for (int i = 0; i <= n; i++) {
+    int rc = 0;
+    for (int i = 0; i <= n && !rc; i++) {
         if (i < n) {
-            if (!in0[i] || !in1[i] || !out[i]) { last_error = "null frame pointer"; return -1; }
             if (ts[i] == 0.f || ts[i] == 1.f) {
                 if (out[i] != (ts[i] == 0.f ? in0[i] : in1[i])) memcpy(out[i], ts[i] == 0.f ? in0[i] : in1[i], nb);  // host-side copy, touches nothing queued
                 continue;
             }
             const int s = chunk % nslots;
-            if (cn == 0) {
-                if (used[s]) cudaStreamWaitEvent(st_copy_[0], ev_comp_[s], 0);  // inputs of slot s are free once its compute finished
-                nup = 0;
-            }
-            // a frame shared by consecutive pairs of the chunk (pair k's in1 is pair k+1's in0 in a stream) is uploaded once:
-            // the slot holds up to 2*B distinct input frames, found again by host pointer
+            if (cn == 0) nfe = 0;
             const uint8_t* hp2[2] = {in0[i], in1[i]};
-            const uint8_t* dp2[2];
-            for (int k = 0; k < 2; k++) {
-                int found = -1;
-                for (int u = 0; u < nup; u++)
-                    if (up_host[u] == hp2[k]) { found = u; break; }
-                if (found < 0) {
-                    DevBuf& bi = buf(s, nup >> 1, nup & 1);
-                    if (bi.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
-                    cudaMemcpyAsync(bi.p, hp2[k], nb, cudaMemcpyHostToDevice, st_copy_[0]);
+            const uint8_t* dp2[2] = {nullptr, nullptr};
+            for (int k = 0; k < 2 && !rc; k++) {
+                bool hit = false;
+                FrameEntry* f = frame_lookup(hp2[k], nb, fe, nfe, &hit);
+                if (!f || (!hit && f->buf.ensure(nb))) { set_error("cudaMalloc failed"); rc = -2; break; }
+                if (!hit) {
+                    if (f->reading) cudaStreamWaitEvent(st_copy_[0], f->read_done, 0);  // the previous content is still being read by a lane
+                    f->reading = false;
+                    cudaMemcpyAsync(f->buf.p, hp2[k], nb, cudaMemcpyHostToDevice, st_copy_[0]);
                     g_h2d_bytes += nb;
-                    up_host[nup] = hp2[k];
-                    up_dev[nup] = bi.u8();
-                    found = nup++;
-                }
-                dp2[k] = up_dev[found];
+                } else frame_hits_++;
+                bool listed = false;
+                for (int u = 0; u < nfe; u++) listed = listed || fe[u] == f;
+                if (!listed) fe[nfe++] = f;
+                dp2[k] = f->buf.u8();
             }
-            DevBuf& b2 = buf(s, cn, 2);
-            if (b2.ensure(nb)) { last_error = "cudaMalloc failed"; return -2; }
-            const uint8_t* b0p = dp2[0];
-            const uint8_t* b1p = dp2[1];
-            c0[cn] = b0p; c1[cn] = b1p; co[cn] = b2.u8(); ho[cn] = out[i]; ct[cn] = ts[i];
+            if (rc) break;
+            DevBuf& b2 = out_u8_[(size_t)s * V46_MAX_BATCH + cn];
+            if (b2.ensure(nb)) { set_error("cudaMalloc failed"); rc = -2; break; }
+            c0[cn] = dp2[0]; c1[cn] = dp2[1]; co[cn] = b2.u8(); ho[cn] = out[i]; ct[cn] = ts[i];
             cn++;
         }
         if (cn == per || (i == n && cn > 0)) {
@@ -482,8 +585,9 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             cudaStreamWaitEvent(L.st, ev_h2d_[s], 0);
             if (used[s]) cudaStreamWaitEvent(L.st, ev_d2h_[s], 0);  // output buffers of slot s have been downloaded
             int r = run_chunk(L, cn, c0, c1, w, h, ct, co, L.st);
-            if (r) return r;
+            if (r) { rc = r; break; }
             cudaEventRecord(ev_comp_[s], L.st);
+            for (int u = 0; u < nfe; u++) { cudaEventRecord(fe[u]->read_done, L.st); fe[u]->reading = true; }
             cudaStreamWaitEvent(st_copy_[1], ev_comp_[s], 0);
             for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, st_copy_[1]);
             g_d2h_bytes += (unsigned long long)cn * nb;
@@ -493,27 +597,31 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             chunk++;
         }
     }
+    // everything queued by this call finishes before it returns -- also on the error paths, where the caller is about to
+    // reuse or free its buffers
     cudaError_t e = cudaStreamSynchronize(st_copy_[0]);
     for (Lane* L : lanes_) { cudaError_t e2 = cudaStreamSynchronize(L->st); if (e2 != cudaSuccess) e = e2; }
     cudaError_t e3 = cudaStreamSynchronize(st_copy_[1]);
     if (e3 != cudaSuccess) e = e3;
-    if (e != cudaSuccess) { last_error = std::string("CUDA failure: ") + cudaGetErrorString(e); return -2; }
+    for (auto& f : frames_) { f.reading = false; if (!frame_cache_ || rc) f.host = nullptr; }
+    if (rc) { cudaGetLastError(); return rc; }
+    if (e != cudaSuccess) { set_error(std::string("CUDA failure: ") + cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
 int Engine::run_device(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
-    if (fast_ok_ && use_fast_ && L.fast && v4_ && !tta_ && !ttat_ && precision_ == 1) {
+    if (fast_usable() && L.fast) {
         std::string err;
         int r = L.fast->run(d_in0, d_in1, w, h, t, d_out, st, err);
-        if (r) { last_error = err; return -5; }
+        if (r) { set_error(err); return -5; }
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
+        if (e != cudaSuccess) { set_error(std::string("kernel launch failure: ") + cudaGetErrorString(e)); return -2; }
         return 0;
     }
     int r = v4_ ? run_v4(L, d_in0, d_in1, w, h, t, d_out, st) : run_v1v2(L, d_in0, d_in1, w, h, d_out, st);
     if (r) return r;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { last_error = std::string("kernel launch failure: ") + cudaGetErrorString(e); return -2; }
+    if (e != cudaSuccess) { set_error(std::string("kernel launch failure: ") + cudaGetErrorString(e)); return -2; }
     return 0;
 }
 
@@ -528,13 +636,13 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
     std::vector<Tensor> o;
     const int nti = tta_ ? 8 : 1;
     Tensor I0[8], I1[8], T[2], TR[2];
+    if (L.pad0.ensure((size_t)nti * 3 * plane * 4) || L.pad1.ensure((size_t)nti * 3 * plane * 4)) { set_error("cudaMalloc failed"); return -2; }
+    launch_preproc(d_in0, w, h, L.pad0.f(), wp, hp, nti, bgr_, st);  // rife.cpp:4152-4211 / 3253-3413: all orientations from one read
+    launch_preproc(d_in1, w, h, L.pad1.f(), wp, hp, nti, bgr_, st);
     for (int ti = 0; ti < nti; ti++) {
-        if (L.pad0[ti].ensure(3 * plane * 4) || L.pad1[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
-        launch_preproc(d_in0, w, h, L.pad0[ti].f(), wp, hp, ti, st);  // rife.cpp:4152-4211 / 3253-3413
-        launch_preproc(d_in1, w, h, L.pad1[ti].f(), wp, hp, ti, st);
         int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
-        I0[ti] = Tensor::chw(L.pad0[ti].f(), 3, th, tw);
-        I1[ti] = Tensor::chw(L.pad1[ti].f(), 3, th, tw);
+        I0[ti] = Tensor::chw(L.pad0.f() + (size_t)ti * 3 * plane, 3, th, tw);
+        I1[ti] = Tensor::chw(L.pad1.f() + (size_t)ti * 3 * plane, 3, th, tw);
     }
     L.ts[0].ensure(plane * 4);
     launch_fill(L.ts[0].f(), plane, t, st);  // full padded plane, rife.cpp:4213-4214
@@ -551,9 +659,9 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
     if (!tta_ && !ttat_) {
         // rife.cpp:4345-4351
         Inputs in = {{"in0", I0[0]}, {"in1", I1[0]}, {"in2", T[0]}};
-        if (F.run(in, {"out0"}, o, st, err)) { last_error = err; return -5; }
+        if (F.run(in, {"out0"}, o, st, err)) { set_error(err); return -5; }
         const float* ins[1] = {o[0].p};
-        launch_postproc(ins, nullptr, 1, wp, hp, d_out, w, h, 1, st);  // rife.cpp:4375-4398
+        launch_postproc(ins, 1, wp, hp, d_out, w, h, cpu_crop_quirk_, bgr_, st);  // rife.cpp:4375-4398
         return 0;
     }
 
@@ -563,13 +671,13 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
             {   // rife.cpp:3432-3451 / 4233-4252: inject the already merged flow0..fi-1, extract flow<fi>
                 Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], fl[k][ti]});
-                if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
+                if (F.run(in, {kFlow[fi]}, o, st, err)) { set_error(err); return -5; }
                 fl[fi][ti] = keep(o[0], L.flow[fi][ti], st);
             }
             if (ttat_) {
                 Inputs in = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], flr[k][ti]});
-                if (F.run(in, {kFlow[fi]}, o, st, err)) { last_error = err; return -5; }
+                if (F.run(in, {kFlow[fi]}, o, st, err)) { set_error(err); return -5; }
                 flr[fi][ti] = keep(o[0], L.flowr[fi][ti], st);
                 // rife.cpp:3476-3512 / 4277-4312
                 launch_temporal_merge_v2(fl[fi][ti].p, flr[fi][ti].p, (size_t)fl[fi][ti].h * fl[fi][ti].w, 1, st);
@@ -586,23 +694,20 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
         }
     }
     const float* ins[16];
-    int orients[16];
     for (int ti = 0; ti < nti; ti++) {
         Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
         for (int k = 0; k < 4; k++) in.push_back({kFlow[k], fl[k][ti]});
-        if (F.run(in, {"out0"}, o, st, err)) { last_error = err; return -5; }
+        if (F.run(in, {"out0"}, o, st, err)) { set_error(err); return -5; }
         ins[ti] = keep(o[0], L.outp[ti], st).p;
-        orients[ti] = ti;
         if (ttat_) {
             Inputs inr = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
             for (int k = 0; k < 4; k++) inr.push_back({kFlow[k], flr[k][ti]});
-            if (F.run(inr, {"out0"}, o, st, err)) { last_error = err; return -5; }
+            if (F.run(inr, {"out0"}, o, st, err)) { set_error(err); return -5; }
             ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
-            orients[nti + ti] = ti;
         }
     }
-    if (tta_) launch_postproc(ins, orients, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, st);  // rife.cpp:4060-4144
-    else launch_postproc(ins, nullptr, 2, wp, hp, d_out, w, h, 1, st);                    // rife.cpp:4356-4371
+    if (tta_) launch_postproc(ins, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, bgr_, st);  // rife.cpp:4060-4144
+    else launch_postproc(ins, 2, wp, hp, d_out, w, h, cpu_crop_quirk_, bgr_, st);       // rife.cpp:4356-4371
     return 0;
 }
 
@@ -617,13 +722,13 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
     std::vector<Tensor> o;
     const int nti = tta_ ? 8 : 1;
     Tensor I0[8], I1[8];
+    if (L.pad0.ensure((size_t)nti * 3 * plane * 4) || L.pad1.ensure((size_t)nti * 3 * plane * 4)) { set_error("cudaMalloc failed"); return -2; }
+    launch_preproc(d_in0, w, h, L.pad0.f(), wp, hp, nti, bgr_, st);  // rife.cpp:4152-4211 / 3253-3413: all orientations from one read
+    launch_preproc(d_in1, w, h, L.pad1.f(), wp, hp, nti, bgr_, st);
     for (int ti = 0; ti < nti; ti++) {
-        if (L.pad0[ti].ensure(3 * plane * 4) || L.pad1[ti].ensure(3 * plane * 4)) { last_error = "cudaMalloc failed"; return -2; }
-        launch_preproc(d_in0, w, h, L.pad0[ti].f(), wp, hp, ti, st);
-        launch_preproc(d_in1, w, h, L.pad1[ti].f(), wp, hp, ti, st);
         int th = ti < 4 ? hp : wp, tw = ti < 4 ? wp : hp;
-        I0[ti] = Tensor::chw(L.pad0[ti].f(), 3, th, tw);
-        I1[ti] = Tensor::chw(L.pad1[ti].f(), 3, th, tw);
+        I0[ti] = Tensor::chw(L.pad0.f() + (size_t)ti * 3 * plane, 3, th, tw);
+        I1[ti] = Tensor::chw(L.pad1.f() + (size_t)ti * 3 * plane, 3, th, tw);
     }
     // flownet(a, b) -> flow at half resolution; uhd: rife.cpp:2212-2229
     auto flownet = [&](const Tensor& a, const Tensor& b, DevBuf& dst, Tensor& flow) -> int {
@@ -636,7 +741,7 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
             launch_interp_bilinear(a.p, 3, a.h, a.w, ad.p, ad.h, ad.w, st);
             launch_interp_bilinear(b.p, 3, b.h, b.w, bd.p, bd.h, bd.w, st);
             Inputs in = {{"input0", ad}, {"input1", bd}};
-            if (F.run(in, {"flow"}, o, st, err)) { last_error = err; return -5; }
+            if (F.run(in, {"flow"}, o, st, err)) { set_error(err); return -5; }
             Tensor fd = o[0];
             flow = Tensor::chw(nullptr, fd.c, (int)(fd.h * 2.f), (int)(fd.w * 2.f));
             dst.ensure(flow.count() * 4);
@@ -645,7 +750,7 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
             launch_unary(flow.p, flow.p, flow.count(), U_MUL_S, 2.f, 0.f, st);
         } else {
             Inputs in = {{"input0", a}, {"input1", b}};
-            if (F.run(in, {"flow"}, o, st, err)) { last_error = err; return -5; }
+            if (F.run(in, {"flow"}, o, st, err)) { set_error(err); return -5; }
             flow = keep(o[0], dst, st);
         }
         return 0;
@@ -675,7 +780,6 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
     }
     static const char* kCtx[4] = {"f1", "f2", "f3", "f4"};
     const float* ins[16];
-    int orients[16];
     for (int ti = 0; ti < nti; ti++) {
         Tensor c0[4], c1[4];
         Tensor f0 = fl[ti], f1 = fl[ti];
@@ -686,31 +790,29 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
         }
         {   // rife.cpp:2335-2351
             Inputs in = {{"input.1", I0[ti]}, {"flow.0", f0}};
-            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
+            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { set_error(err); return -5; }
             for (int k = 0; k < 4; k++) c0[k] = keep(o[k], L.ctx[0][k], st);
         }
         {   // rife.cpp:2352-2368
             Inputs in = {{"input.1", I1[ti]}, {v2_ ? "flow.0" : "flow.1", f1}};
-            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { last_error = err; return -5; }
+            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { set_error(err); return -5; }
             for (int k = 0; k < 4; k++) c1[k] = keep(o[k], L.ctx[1][k], st);
         }
         {   // rife.cpp:2372-2388
             Inputs in = {{"img0", I0[ti]}, {"img1", I1[ti]}, {"flow", fl[ti]}, {"3", c0[0]}, {"4", c0[1]}, {"5", c0[2]}, {"6", c0[3]},
                          {"7", c1[0]}, {"8", c1[1]}, {"9", c1[2]}, {"10", c1[3]}};
-            if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
+            if (U.run(in, {"output"}, o, st, err)) { set_error(err); return -5; }
             ins[ti] = (tta_ || ttat_) ? keep(o[0], L.outp[ti], st).p : o[0].p;
-            orients[ti] = ti;
-        }
+            }
         if (ttat_) {  // rife.cpp:2391-2409
             Inputs in = {{"img0", I1[ti]}, {"img1", I0[ti]}, {"flow", flr[ti]}, {"3", c1[0]}, {"4", c1[1]}, {"5", c1[2]}, {"6", c1[3]},
                          {"7", c0[0]}, {"8", c0[1]}, {"9", c0[2]}, {"10", c0[3]}};
-            if (U.run(in, {"output"}, o, st, err)) { last_error = err; return -5; }
+            if (U.run(in, {"output"}, o, st, err)) { set_error(err); return -5; }
             ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
-            orients[nti + ti] = ti;
         }
     }
-    if (tta_) launch_postproc(ins, orients, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, st);
-    else launch_postproc(ins, nullptr, ttat_ ? 2 : 1, wp, hp, d_out, w, h, 1, st);
+    if (tta_) launch_postproc(ins, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, bgr_, st);
+    else launch_postproc(ins, ttat_ ? 2 : 1, wp, hp, d_out, w, h, cpu_crop_quirk_, bgr_, st);
     return 0;
 }
 

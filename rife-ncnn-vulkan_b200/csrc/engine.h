@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -29,8 +31,9 @@ struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     NetRunner* run[3] = {nullptr, nullptr, nullptr};
-    V46Runner* fast = nullptr;  // hand-scheduled rife-v4.6 path (plain mode, precision tier 1)
-    DevBuf pad0[8], pad1[8], ts[2], tsr[2];
+    V46Runner* fast = nullptr;  // hand-scheduled rife-v4 / v4.6 path (plain mode, precision tier 1)
+    DevBuf pad0, pad1;          // the 8 orientations of the two padded frames, planar fp32 (generic path)
+    DevBuf ts[2], tsr[2];
     DevBuf flow[4][8], flowr[4][8];
     DevBuf outp[16];
     DevBuf ctx[2][4];
@@ -48,7 +51,7 @@ public:
     int init();  // selects the device, creates streams
     int load(const std::string& modeldir);
     int load_packed(const void* blob, size_t bytes);
-    const std::string& packed() const { return packed_; }
+    std::string packed() const { std::lock_guard<std::mutex> lk(mu_); return packed_; }
     int process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out);
     int process_device(const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out);
     int process_batch(int n, const uint8_t* const* in0, const uint8_t* const* in1, int w, int h, const float* ts, uint8_t* const* out);
@@ -63,41 +66,69 @@ public:
     };
     int get_option(const std::string& key, int* value);
     void set_stream(cudaStream_t s) { std::lock_guard<std::mutex> lk(mu_); user_stream_ = s; use_user_stream_ = s != nullptr; }
-    std::string last_error;
+    std::string stage_report();         // option "ktime": per-lane, per-stage times of the fused path
+    void forget_frames();               // drops every cached input frame (option "frame_cache")
+    std::string last_error() const { std::lock_guard<std::mutex> lk(err_mu_); return last_error_; }
 
 private:
-    int finish_load();
     int run_device(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
     int run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
     int run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st);
     int make_lanes(int n);
     void setup_fast();      // (re)creates the per-lane fast runners and validates them against the generic executor
     Tensor keep(const Tensor& t, DevBuf& b, cudaStream_t st);  // copy a plan-owned tensor into an engine buffer
+    void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu_); last_error_ = s; }
+    void sync_all();        // error paths: nothing of this handle may still touch caller buffers after an error return
+    void publish();         // refreshes the lock-free snapshot process_host() reads (call with mu_ held)
+    bool fast_usable() const { return fast_ok_ && use_fast_ && v4_ && !tta_ && !ttat_ && precision_ == 1; }
 
     int gpuid_;
     bool tta_, ttat_, uhd_, v2_, v4_;
     bool loaded_ = false;
     int precision_ = 1;
     bool async_ = false;
-    bool fast_ok_ = false;  // the fused v4.6 path reproduced the generic executor on the self-check
+    bool fast_ok_ = false;  // the fused path reproduced the generic executor on the self-check
     int use_fast_ = 1;
     int plain_mask_ = 12;  // IFBlocks 2 and 3 (80 % of the FLOPs): plain fp16 activations in the residual chain (profiles/r1_precision_study_plain_blocks.txt)
     int combine_ = COMBINE_DEFAULT;  // concurrent process() calls on this handle are executed as one lock-step batch (combiner.h)
+    int cpu_crop_quirk_ = 0;  // 1: reproduce the reference CPU path's contiguous read of the padded output (rife.cpp:4375-4387)
+    int bgr_ = 0;             // frames are B,G,R in memory (the reference's Windows build: rife_preproc.comp:13,53-56)
     Combiner<HostReq> combiner_;
     int run_combined(HostReq** rq, int n);
     int recompute_fm_ = RECOMPUTE_FM_DEFAULT;  // fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2: fused_v46.h)
     cudaStream_t user_stream_ = nullptr;
     bool use_user_stream_ = false;
-    Net nets_[3];           // flownet, contextnet, fusionnet
+    std::unique_ptr<Net> nets_[3];  // flownet, contextnet, fusionnet
     std::vector<Lane*> lanes_;
     int nlanes_ = 2;
     std::string packed_;    // serialized model (param text + bin bytes per net)
     cudaStream_t st_copy_[2] = {nullptr, nullptr};
     static const int kSlots = 8;
     cudaEvent_t ev_h2d_[kSlots] = {}, ev_comp_[kSlots] = {}, ev_d2h_[kSlots] = {}, ev_entry_ = nullptr;
-    std::mutex mu_;
+    mutable std::mutex mu_;
+    mutable std::mutex err_mu_;
+    std::string last_error_;
+    // What process_host() needs to decide whether a call goes through the combiner, readable without mu_ (the leader of a
+    // combined batch holds mu_ for the whole batch; followers must be able to queue meanwhile).
+    std::atomic<int> snap_combine_{0}, snap_fast_{0}, snap_batch_{0}, snap_lanes_{1};
     // device buffers
-    std::vector<DevBuf> u8_;  // staged in0,in1,out per pipeline slot and batch position
+    std::vector<DevBuf> out_u8_;  // staged outputs per pipeline slot and batch position
+    // Input frames on the device, found again by host pointer.  Within one call a frame shared by
+    // several pairs is uploaded once; with option "frame_cache" = 1 entries survive across calls (the caller promises not to
+    // modify a frame buffer it has handed in until it calls forget_frames / turns the option off).
+    struct FrameEntry {
+        const uint8_t* host = nullptr;
+        size_t nb = 0;
+        DevBuf buf;
+        cudaEvent_t read_done = nullptr;  // last compute that read buf (recorded on a lane stream)
+        bool reading = false;
+        unsigned long long stamp = 0;
+    };
+    std::vector<FrameEntry> frames_;
+    unsigned long long frame_clock_ = 0;
+    int frame_cache_ = 0;
+    unsigned long long frame_hits_ = 0;
+    FrameEntry* frame_lookup(const uint8_t* host, size_t nb, FrameEntry* const* cur, int ncur, bool* hit);
     int batch_ = 0;           // pairs per lock-step batch on the fused path (0 = choose from the frame size)
     int batch_for(int w, int h) const;
     int run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st);

@@ -74,6 +74,7 @@ int NetRunner::init(const Net* net, std::string& err) {
         } else if (L.type == "Deconvolution") {
             int cout = L.geti(0, 0), kw = L.geti(1, 0), kh = L.geti(11, kw);
             if (kw != 4 || kh != 4 || L.geti(3, 1) != 2 || L.geti(4, 0) != 1) { err = "unsupported deconvolution shape in " + L.name; return -4; }
+            if (cout <= 0 || L.weight.empty() || L.weight.size() % ((size_t)cout * 16)) { err = "bad deconv weights in " + L.name; return -4; }
             int cin = (int)(L.weight.size() / ((size_t)cout * 16));
             int ocpad = (cout + 63) / 64 * 64;
             // deconvolution.cpp:68-141: out[y = i*2 + ky - 1] += in[i] * w[oc][ic][ky][kx].  Gather form per output
@@ -286,8 +287,9 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             const ParamVal* st = L.get(9);
             const ParamVal* en = L.get(10);
             const ParamVal* ax = L.get(11);
-            if (!st || !en || !ax || ax->ai.size() != 1 || ax->ai[0] != 0 || in(0).dims != 3) { err = "unsupported Crop form in " + L.name; return -23; }
+            if (!st || !en || !ax || ax->ai.size() != 1 || ax->ai[0] != 0 || st->ai.size() != 1 || en->ai.size() != 1 || in(0).dims != 3) { err = "unsupported Crop form in " + L.name; return -23; }
             int s0 = st->ai[0], e0 = std::min(en->ai[0], in(0).c);  // crop.cpp:387-430 (end clamps to the extent)
+            if (s0 < 0 || s0 >= e0) { err = "bad Crop range in " + L.name; return -23; }
             o = in(0);
             o.c = e0 - s0;
             plan.blobs[L.tops[0]] = o;
@@ -304,12 +306,15 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             }
         } else if (T == "Convolution") {
             int k = L.geti(1, 0), sd = L.geti(3, 1), pad = L.geti(4, 0);
-            if (L.geti(11, k) != k || L.geti(13, sd) != sd || L.geti(2, 1) != 1) { err = "unsupported conv form in " + L.name; return -23; }
+            if (L.geti(11, k) != k || L.geti(13, sd) != sd || L.geti(2, 1) != 1 || k <= 0 || sd <= 0) { err = "unsupported conv form in " + L.name; return -23; }
             o.c = L.geti(0, 0);
+            // the kernels index the weights by the input's channel count: it must be the one the weights were stored for
+            if (o.c <= 0 || (size_t)in(0).c * o.c * k * k != L.weight.size() || in(0).dims != 3) { err = "conv input channels do not match the weights in " + L.name; return -23; }
             o.h = (in(0).h + 2 * pad - k) / sd + 1;  // convolution.cpp: outh = (h - kernel_extent) / stride + 1 after padding
             o.w = (in(0).w + 2 * pad - k) / sd + 1;
         } else if (T == "Deconvolution") {
             o.c = L.geti(0, 0);
+            if (o.c <= 0 || (size_t)in(0).c * o.c * 16 != L.weight.size() || in(0).dims != 3) { err = "deconv input channels do not match the weights in " + L.name; return -23; }
             o.h = (in(0).h - 1) * 2 + 4 - 2;  // deconvolution.cpp:183-188 (crop by pad on every side)
             o.w = (in(0).w - 1) * 2 + 4 - 2;
         } else if (T == "Interp") {
@@ -343,6 +348,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             o.w = in(0).c;
             o.c = o.h = 1;
         } else if (T == "InnerProduct") {
+            if (L.geti(0, 0) <= 0 || in(0).count() * (size_t)L.geti(0, 0) != L.weight.size()) { err = "InnerProduct input size does not match the weights in " + L.name; return -23; }
             o.dims = 1;
             o.w = L.geti(0, 0);
             o.c = o.h = 1;

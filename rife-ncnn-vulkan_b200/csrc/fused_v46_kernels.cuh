@@ -164,18 +164,20 @@ struct SrcBatch {
     const uint8_t* p[2 * V46_MAX_BATCH];
 };
 // rife_preproc without the float conversion: RGB u8 HWC (w x h) -> RGBX [hp][wp], zeros outside the image
-__global__ void rgbx_kernel(const __grid_constant__ SrcBatch sb, int w, int h, int wp, int hp, uchar4* __restrict__ out) {
+// bgr != 0: the frame bytes are B,G,R (the reference's Windows build, rife_preproc.comp:13,53-56); RGBX is always R,G,B,0
+__global__ void rgbx_kernel(const __grid_constant__ SrcBatch sb, int w, int h, int wp, int hp, uchar4* __restrict__ out, int bgr) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= wp) return;
     uchar4 q = make_uchar4(0, 0, 0, 0);
     if (x < w && y < h) {
         const uint8_t* p = sb.p[blockIdx.z] + ((size_t)y * w + x) * 3;
-        q = make_uchar4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0);
+        q = make_uchar4(__ldg(p + (bgr ? 2 : 0)), __ldg(p + 1), __ldg(p + (bgr ? 0 : 2)), 0);
     }
     out[((size_t)blockIdx.z * hp + y) * wp + x] = q;
 }
 // same, four pixels per thread: 12 source bytes as three aligned words -> one 16-byte store (w % 4 == 0, 4-byte aligned frames)
-__global__ void rgbx4_kernel(const __grid_constant__ SrcBatch sb, int w, int h, int wp, int hp, uchar4* __restrict__ out) {
+__device__ __forceinline__ uint32_t swap_rb(uint32_t v) { return (v & 0xff00ff00u) | ((v & 0xffu) << 16) | ((v >> 16) & 0xffu); }
+__global__ void rgbx4_kernel(const __grid_constant__ SrcBatch sb, int w, int h, int wp, int hp, uchar4* __restrict__ out, int bgr) {
     int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x >= wp) return;
     uint4 o = make_uint4(0, 0, 0, 0);
@@ -186,6 +188,7 @@ __global__ void rgbx4_kernel(const __grid_constant__ SrcBatch sb, int w, int h, 
         o.y = (a >> 24) | ((b & 0xffffu) << 8);
         o.z = (b >> 16) | ((c & 0xffu) << 16);
         o.w = c >> 8;
+        if (bgr) { o.x = swap_rb(o.x); o.y = swap_rb(o.y); o.z = swap_rb(o.z); o.w = swap_rb(o.w); }
     }
     *reinterpret_cast<uint4*>(out + ((size_t)blockIdx.z * hp + y) * wp + x) = o;
 }
@@ -230,7 +233,9 @@ __global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_co
 template <int S, int SP, int MODE, int SPP, bool STORE>
 __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __restrict__ F, float* __restrict__ M, const float* __restrict__ d, int dh, int dw,
                                    const float* __restrict__ dprev, int pdh, int pdw, const float* __restrict__ dpp, int ppdh, int ppdw,
-                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out, int dch) {
+    // dch = planes per image of the block outputs d / dprev / dpp: 6 for rife-v4.6 (PixelShuffle of 24 channels, the sixth
+    // plane unused), 5 for rife-v4 (the deconvolution's own 5 channels at half the block resolution, so SP = 2 * S_{k-1})
     constexpr bool FIRST = MODE == 0;
     static_assert(!(STORE && MODE == 0), "MODE 0 never stores");
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
@@ -241,11 +246,11 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
     const Frame I0 = {ib.p0[b], wp}, I1 = {ib.p1[b], wp};
     F += (size_t)b * 4 * plane;
     M += (size_t)b * plane;
-    d += (size_t)b * 6 * dplane;
+    d += (size_t)b * dch * dplane;
     const size_t pdplane = (size_t)pdh * pdw;
-    if (MODE == 1 || MODE == 3) dprev += (size_t)b * 6 * pdplane;
+    if (MODE == 1 || MODE == 3) dprev += (size_t)b * dch * pdplane;
     const size_t ppdplane = (size_t)ppdh * ppdw;
-    if (MODE == 3) dpp += (size_t)b * 6 * ppdplane;
+    if (MODE == 3) dpp += (size_t)b * dch * ppdplane;
     out += (size_t)b * 16 * oh * ow * 2;
     constexpr int T0 = S == 1 ? 0 : S / 2 - 1;  // first tap inside the footprint (S = 4: 1, S = 2: 0)
     constexpr int NT = S == 1 ? 1 : 2;
@@ -422,26 +427,32 @@ __device__ __forceinline__ void up5(const float* __restrict__ d, int dh, int dw,
 #pragma unroll
     for (int c = 0; c < 5; c++) u[c] = bilerp(d + c * dpl, dw, sy, sx, 1.f - fx, fx, 1.f - fy, fy);
 }
-template <int RC>
+// D3S = 1: d3 is at full resolution (rife-v4.6: flownet.param:202-207, plain adds).  D3S = 2: d3 is the 5-channel deconvolution
+// output at half resolution (rife-v4: models/rife-v4/flownet.param:152-160): U = bilinear(d3, 2), F3 = F*1 + U*2, M3 = M + U[4].
+template <int RC, int D3S>
 __global__ void tail_kernel(const __grid_constant__ InBatch ib, const float* __restrict__ F, const float* __restrict__ M, const float* __restrict__ d3, int hp, int wp,
                             const __grid_constant__ OutBatch ob,
-                            int w, int h, const __grid_constant__ DSrc ds) {
+                            int w, int h, const __grid_constant__ DSrc ds, int contig, int dch, int bgr) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const int b = blockIdx.z;
     {
         const size_t pl = (size_t)hp * wp;
-        F += (size_t)b * 4 * pl; M += (size_t)b * pl; d3 += (size_t)b * 6 * pl;
+        F += (size_t)b * 4 * pl; M += (size_t)b * pl; d3 += (size_t)b * dch * (pl / (D3S * D3S));
     }
     const Frame I0 = {ib.p0[b], wp}, I1 = {ib.p1[b], wp};
     uint8_t* __restrict__ rgb = ob.p[b];
-    // the reference CPU path reads the first w*h floats of each padded output channel contiguously (rife.cpp:4375-4387)
+    // Crop of the padded output: output pixel (y, x) is padded pixel (y, x), as rife_postproc.comp:42 does (gy * p.w + gx on
+    // the padded width).  contig != 0 (option "cpu_crop_quirk") reproduces the reference's CPU path instead, which reads the
+    // first w*h floats of each padded channel contiguously (rife.cpp:4375-4387): a sheared frame whenever w % 32 != 0.
     const uint32_t idx = (uint32_t)y * (uint32_t)w + (uint32_t)x;  // < 2^31: w * h pixels of one frame
-    const int Y = w == wp ? y : (int)(idx / (uint32_t)wp), X = w == wp ? x : (int)(idx - (uint32_t)Y * (uint32_t)wp);
+    const bool same = w == wp || !contig;
+    const int Y = same ? y : (int)(idx / (uint32_t)wp), X = same ? x : (int)(idx - (uint32_t)Y * (uint32_t)wp);
     const size_t plane = (size_t)hp * wp, pi = (size_t)Y * wp + X;
     float fo[4], mo;  // F, M after block 2
     if (RC == 2) {
         float u[5];
+        static_assert(RC == 0 || D3S == 1, "the recompute variants exist for the rife-v4.6 layout only");
         up5<8>(ds.d[0] + (size_t)b * 6 * (hp / 8) * (wp / 8), hp / 8, wp / 8, X, Y, u);
 #pragma unroll
         for (int c = 0; c < 4; c++) fo[c] = u[c] * 8.f;
@@ -462,9 +473,18 @@ __global__ void tail_kernel(const __grid_constant__ InBatch ib, const float* __r
         for (int c = 0; c < 4; c++) fo[c] = fo[c] * 1.f + u[c] * 2.f;
         mo = mo + u[4];
     }
-    const float f0 = fo[0] + d3[pi], f1 = fo[1] + d3[plane + pi];
-    const float f2 = fo[2] + d3[2 * plane + pi], f3 = fo[3] + d3[3 * plane + pi];
-    float m = mo + d3[4 * plane + pi];
+    float f0, f1, f2, f3, m;
+    if (D3S == 1) {
+        f0 = fo[0] + d3[pi]; f1 = fo[1] + d3[plane + pi];
+        f2 = fo[2] + d3[2 * plane + pi]; f3 = fo[3] + d3[3 * plane + pi];
+        m = mo + d3[4 * plane + pi];
+    } else {
+        float u[5];
+        up5<D3S>(d3, hp / D3S, wp / D3S, X, Y, u);
+        f0 = fo[0] * 1.f + u[0] * (float)D3S; f1 = fo[1] * 1.f + u[1] * (float)D3S;  // Eltwise SUM {1, 2}
+        f2 = fo[2] * 1.f + u[2] * (float)D3S; f3 = fo[3] * 1.f + u[3] * (float)D3S;
+        m = mo + u[4];
+    }
     m = fminf(m, 88.3762626647949f);
     m = fmaxf(m, -88.3762626647949f);
     m = 1.f / (1.f + expf(-m));   // sigmoid.cpp:42-44
@@ -481,7 +501,7 @@ __global__ void tail_kernel(const __grid_constant__ InBatch ib, const float* __r
         float w1 = s1[c] * om;
         float v = (w0 + w1) * 255.f + 0.5f;
         int iv = (int)v;
-        o[c] = (uint8_t)min(max(iv, 0), 255);
+        o[bgr ? 2 - c : c] = (uint8_t)min(max(iv, 0), 255);
     }
 }
 

@@ -316,34 +316,6 @@ void launch_pixelshuffle(const float* in, int c, int h, int w, float* out, int r
     g_launch_count++;
 }
 
-// src/warp.cpp:96-168: backward bilinear warp, indices clamped, alpha/beta taken AFTER clamping.
-__global__ void warp_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out, int c, int h, int w) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= w) return;
-    size_t hw = (size_t)h * w, pi = (size_t)y * w + x;
-    float sx = x + flow[pi], sy = y + flow[hw + pi];
-    int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
-    int x1 = x0 + 1, y1 = y0 + 1;
-    x0 = min(max(x0, 0), w - 1);
-    y0 = min(max(y0, 0), h - 1);
-    x1 = min(max(x1, 0), w - 1);
-    y1 = min(max(y1, 0), h - 1);
-    float alpha = sx - x0, beta = sy - y0;
-    for (int q = 0; q < c; q++) {
-        const float* p = img + (size_t)q * hw;
-        float v0 = p[(size_t)y0 * w + x0], v1 = p[(size_t)y0 * w + x1];
-        float v2 = p[(size_t)y1 * w + x0], v3 = p[(size_t)y1 * w + x1];
-        float v4 = v0 * (1 - alpha) + v1 * alpha;
-        float v5 = v2 * (1 - alpha) + v3 * alpha;
-        out[(size_t)q * hw + pi] = v4 * (1 - beta) + v5 * beta;
-    }
-}
-void launch_warp(const float* img, const float* flow, float* out, int c, int h, int w, cudaStream_t st) {
-    warp_kernel<<<dim3(cdiv(w, 128), h), 128, 0, st>>>(img, flow, out, c, h, w);
-    g_launch_count++;
-}
-
 // pooling.cpp:61-105 global average
 __global__ void global_avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, size_t hw) {
     const float* p = in + (size_t)blockIdx.x * hw;
@@ -379,45 +351,7 @@ void launch_innerproduct(const float* in, const float* w, const float* bias, flo
     g_launch_count++;
 }
 
-// ------------------------------------------------------------------------------------------------
-// RIFE stages
-// ------------------------------------------------------------------------------------------------
-// orientation maps (rife.cpp:3340-3364): destination index of padded source pixel (y,x)
-__device__ __forceinline__ size_t orient_index(int o, int y, int x, int wp, int hp) {
-    switch (o) {
-        case 0: return (size_t)y * wp + x;
-        case 1: return (size_t)y * wp + (wp - 1 - x);
-        case 2: return (size_t)(hp - 1 - y) * wp + (wp - 1 - x);
-        case 3: return (size_t)(hp - 1 - y) * wp + x;
-        case 4: return (size_t)x * hp + y;
-        case 5: return (size_t)x * hp + (hp - 1 - y);
-        case 6: return (size_t)(wp - 1 - x) * hp + (hp - 1 - y);
-        default: return (size_t)(wp - 1 - x) * hp + y;
-    }
-}
-
-// rife_preproc.comp:33-66 / rife.cpp:4152-4211: u8 -> float * (1/255), zero outside (w,h)
-__global__ void preproc_kernel(const uint8_t* __restrict__ rgb, int w, int h, float* __restrict__ out, int wp, int hp, int orient) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= wp) return;
-    float v[3] = {0.f, 0.f, 0.f};
-    if (x < w && y < h) {
-        const uint8_t* p = rgb + ((size_t)y * w + x) * 3;
-        v[0] = (float)p[0] * (1 / 255.f);
-        v[1] = (float)p[1] * (1 / 255.f);
-        v[2] = (float)p[2] * (1 / 255.f);
-    }
-    size_t plane = (size_t)wp * hp, di = orient_index(orient, y, x, wp, hp);
-    out[di] = v[0];
-    out[plane + di] = v[1];
-    out[2 * plane + di] = v[2];
-}
-void launch_preproc(const uint8_t* rgb, int w, int h, float* out, int wp, int hp, int orient, cudaStream_t st) {
-    preproc_kernel<<<dim3(cdiv(wp, 128), hp), 128, 0, st>>>(rgb, w, h, out, wp, hp, orient);
-    g_launch_count++;
-}
-
+// (the RIFE-specific HBM stages -- preproc, postproc, TTA averages, warp -- live in hbm_kernels.cu)
 __global__ void fill_kernel(float* p, size_t n, float v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -425,127 +359,6 @@ __global__ void fill_kernel(float* p, size_t n, float v) {
 }
 void launch_fill(float* p, size_t n, float v, cudaStream_t st) {
     fill_kernel<<<min(cdiv(n, 256), 148u * 16), 256, 0, st>>>(p, n, v);
-    g_launch_count++;
-}
-
-struct PostArgs {
-    const float* in[16];
-    int orient[16];
-};
-// rife_postproc.comp:33-63 / rife.cpp:4375-4398 + mat_pixel.cpp:158: v*255+0.5 -> (int) -> clamp -> u8.
-// TTA: rife.cpp:4060-4144: mean of the 8 un-rotated outputs (/8), temporal: (v + vr) * 0.5.
-__global__ void postproc_kernel(PostArgs pa, int n_in, int wp, int hp, uint8_t* __restrict__ rgb, int w, int h, int cpu_contig) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= w) return;
-    size_t plane = (size_t)wp * hp;
-    uint8_t* o = rgb + ((size_t)y * w + x) * 3;
-    for (int q = 0; q < 3; q++) {
-        float v;
-        if (n_in == 1) {
-            // the CPU reference reads the first w*h floats of each padded channel contiguously
-            // (rife.cpp:4375-4387); identical to a proper crop whenever w == wp
-            size_t idx = cpu_contig ? (size_t)y * w + x : (size_t)y * wp + x;
-            v = pa.in[0][q * plane + idx] * 255.f + 0.5f;
-        } else if (n_in == 2) {
-            size_t idx = cpu_contig ? (size_t)y * w + x : (size_t)y * wp + x;
-            v = (pa.in[0][q * plane + idx] + pa.in[1][q * plane + idx]) * 0.5f * 255.f + 0.5f;
-        } else {
-            float s = 0.f;
-            for (int i = 0; i < 8; i++) s += pa.in[i][q * plane + orient_index(pa.orient[i], y, x, wp, hp)];
-            s = s / 8;
-            if (n_in == 16) {
-                float sr = 0.f;
-                for (int i = 8; i < 16; i++) sr += pa.in[i][q * plane + orient_index(pa.orient[i], y, x, wp, hp)];
-                sr = sr / 8;
-                v = (s + sr) * 0.5f * 255.f + 0.5f;
-            } else {
-                v = s * 255.f + 0.5f;
-            }
-        }
-        int iv = (int)v;  // truncation, as mat_pixel.cpp:158 `(uchar)min(max((int)v,0),255)`
-        o[q] = (uint8_t)min(max(iv, 0), 255);
-    }
-}
-void launch_postproc(const float* const* ins, const int* orients, int n_in, int wp, int hp, uint8_t* rgb, int w, int h, int cpu_contig, cudaStream_t st) {
-    PostArgs pa;
-    for (int i = 0; i < 16; i++) {
-        pa.in[i] = i < n_in ? ins[i] : nullptr;
-        pa.orient[i] = i < n_in && orients ? orients[i] : 0;
-    }
-    postproc_kernel<<<dim3(cdiv(w, 128), h), 128, 0, st>>>(pa, n_in, wp, hp, rgb, w, h, cpu_contig);
-    g_launch_count++;
-}
-
-// rife.cpp:2269-2319 (v1 rule) -- rife_flow_tta_temporal_avg.comp:19-42
-__global__ void temporal_merge_v1_kernel(float* f, float* fr, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x = (f[i] - fr[i]) * 0.5f, y = (f[n + i] - fr[n + i]) * 0.5f;
-    f[i] = x; f[n + i] = y;
-    fr[i] = -x; fr[n + i] = -y;
-}
-void launch_temporal_merge_v1(float* f, float* fr, size_t n, cudaStream_t st) {
-    temporal_merge_v1_kernel<<<cdiv(n, 256), 256, 0, st>>>(f, fr, n);
-    g_launch_count++;
-}
-// rife.cpp:2285-2306 (v2 rule), :4290-4311 (v4 adds the mask) -- rife_v2/v4_flow_tta_temporal_avg.comp
-__global__ void temporal_merge_v2_kernel(float* f, float* fr, size_t n, int has_mask) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x = (f[i] + fr[2 * n + i]) * 0.5f;
-    float y = (f[n + i] + fr[3 * n + i]) * 0.5f;
-    float z = (f[2 * n + i] + fr[i]) * 0.5f;
-    float w = (f[3 * n + i] + fr[n + i]) * 0.5f;
-    f[i] = x; f[n + i] = y; f[2 * n + i] = z; f[3 * n + i] = w;
-    fr[i] = z; fr[n + i] = w; fr[2 * n + i] = x; fr[3 * n + i] = y;
-    if (has_mask) {
-        float m = (f[4 * n + i] - fr[4 * n + i]) * 0.5f;
-        f[4 * n + i] = m;
-        fr[4 * n + i] = -m;
-    }
-}
-void launch_temporal_merge_v2(float* f, float* fr, size_t n, int has_mask, cudaStream_t st) {
-    temporal_merge_v2_kernel<<<cdiv(n, 256), 256, 0, st>>>(f, fr, n, has_mask);
-    g_launch_count++;
-}
-
-struct Flow8 {
-    float* f[8];
-};
-// rife.cpp:1541-1719 (v1/v2), :3515-3668 (v4) -- rife_flow_tta_avg.comp / rife_v2_.. / rife_v4_..
-// pair k of channels (2k, 2k+1) is an (x,y) flow; channel 4 (nch == 5) is the mask (plain mean).
-__global__ void flow_tta_avg_kernel(Flow8 F, int nch, int fw, int fh) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;  // x in orientation 0
-    int i = blockIdx.y;                             // y
-    if (j >= fw) return;
-    size_t plane = (size_t)fw * fh;
-    size_t idx[8];
-    for (int o = 0; o < 8; o++) idx[o] = orient_index(o, i, j, fw, fh);
-    int npair = nch >= 4 ? 2 : 1;
-    for (int k = 0; k < npair; k++) {
-        size_t cx = (size_t)(2 * k) * plane, cy = (size_t)(2 * k + 1) * plane;
-        float x = (F.f[0][cx + idx[0]] + -F.f[1][cx + idx[1]] + -F.f[2][cx + idx[2]] + F.f[3][cx + idx[3]] +
-                   F.f[4][cy + idx[4]] + F.f[5][cy + idx[5]] + -F.f[6][cy + idx[6]] + -F.f[7][cy + idx[7]]) * 0.125f;
-        float y = (F.f[0][cy + idx[0]] + F.f[1][cy + idx[1]] + -F.f[2][cy + idx[2]] + -F.f[3][cy + idx[3]] +
-                   F.f[4][cx + idx[4]] + -F.f[5][cx + idx[5]] + -F.f[6][cx + idx[6]] + F.f[7][cx + idx[7]]) * 0.125f;
-        F.f[0][cx + idx[0]] = x;  F.f[1][cx + idx[1]] = -x; F.f[2][cx + idx[2]] = -x; F.f[3][cx + idx[3]] = x;
-        F.f[4][cx + idx[4]] = y;  F.f[5][cx + idx[5]] = -y; F.f[6][cx + idx[6]] = -y; F.f[7][cx + idx[7]] = y;
-        F.f[0][cy + idx[0]] = y;  F.f[1][cy + idx[1]] = y;  F.f[2][cy + idx[2]] = -y; F.f[3][cy + idx[3]] = -y;
-        F.f[4][cy + idx[4]] = x;  F.f[5][cy + idx[5]] = x;  F.f[6][cy + idx[6]] = -x; F.f[7][cy + idx[7]] = -x;
-    }
-    if (nch == 5) {
-        size_t cm = 4 * plane;
-        float m = 0.f;
-        for (int o = 0; o < 8; o++) m += F.f[o][cm + idx[o]];
-        m *= 0.125f;
-        for (int o = 0; o < 8; o++) F.f[o][cm + idx[o]] = m;
-    }
-}
-void launch_flow_tta_avg(float* const* f8, int nch, int fw, int fh, cudaStream_t st) {
-    Flow8 F;
-    for (int i = 0; i < 8; i++) F.f[i] = f8[i];
-    flow_tta_avg_kernel<<<dim3(cdiv(fw, 128), fh), 128, 0, st>>>(F, nch, fw, fh);
     g_launch_count++;
 }
 

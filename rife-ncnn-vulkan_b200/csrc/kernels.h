@@ -46,15 +46,17 @@ void launch_warp(const float* img, const float* flow, float* out, int c, int h, 
 void launch_global_avgpool(const float* in, float* out, int c, size_t hw, cudaStream_t st);
 void launch_innerproduct(const float* in, const float* w, const float* bias, float* out, int nin, int nout, int act, float p0, cudaStream_t st);
 
-// ---- RIFE stages ----
-// u8 HWC RGB -> planar float [3][hp][wp] * (1/255), zero outside (w,h).  orient = TTA orientation 0..7
-// (Appendix B index maps); for orient >= 4 the output plane is [3][wp][hp].
-void launch_preproc(const uint8_t* rgb, int w, int h, float* out, int wp, int hp, int orient, cudaStream_t st);
+// ---- RIFE stages, hbm_kernels.cu ----
+// u8 HWC -> planar float * (1/255), zero outside (w,h), for the first `norient` (1 or 8) TTA orientations (Appendix B index
+// maps) from one read of the frame: orientation o at out + o * 3 * wp * hp, as [3][hp][wp] (o < 4) or [3][wp][hp] (o >= 4).
+// bgr: the frame bytes are B,G,R (the reference's Windows build); the planes are always R,G,B.
+void launch_preproc(const uint8_t* rgb, int w, int h, float* out, int wp, int hp, int norient, int bgr, cudaStream_t st);
 void launch_fill(float* p, size_t n, float v, cudaStream_t st);
-// planar float -> u8 HWC: v*255+0.5, trunc, clamp.  n_in inputs (1, 2, 8 or 16) are un-rotated by their
-// orientation (orients[i]) and averaged with scale 1/n_in before quantisation.
-// cpu_quirk_stride: row stride used to read input 0 when no TTA (reference CPU reads w*h contiguous floats).
-void launch_postproc(const float* const* ins, const int* orients, int n_in, int wp, int hp, uint8_t* rgb, int w, int h, int cpu_contig, cudaStream_t st);
+// planar float -> u8 HWC: v*255+0.5, trunc, clamp.  n_in = 1 (plain), 2 (temporal TTA: mean of two), 8 / 16 (spatial TTA:
+// input i is orientation i & 7, un-rotated and averaged; 16 = both temporal directions).
+// cpu_contig (n_in <= 2 only): read the first w*h floats of every padded channel contiguously, as the reference's CPU path
+// does (rife.cpp:4375-4387), instead of cropping the padded rows.
+void launch_postproc(const float* const* ins, int n_in, int wp, int hp, uint8_t* rgb, int w, int h, int cpu_contig, int bgr, cudaStream_t st);
 // temporal merges (in place), n = elements per channel
 void launch_temporal_merge_v1(float* f, float* fr, size_t n, cudaStream_t st);            // 2 ch: (x - xr)/2 ; rev = -x
 void launch_temporal_merge_v2(float* f, float* fr, size_t n, int has_mask, cudaStream_t st); // 4 ch (+ mask at ch 4)

@@ -16,6 +16,8 @@ struct Api {
     int (*device_count)(void);
     int (*create)(rife_b200_t**, int, int, int, int, int, int, int);
     int (*load)(rife_b200_t*, const char*);
+    int (*load_w)(rife_b200_t*, const wchar_t*);
+    int (*set_option)(rife_b200_t*, const char*, int);
     int (*process)(rife_b200_t*, const unsigned char*, const unsigned char*, int, int, float, unsigned char*);
     const char* (*last_error)(rife_b200_t*);
     void (*destroy)(rife_b200_t*);
@@ -43,6 +45,8 @@ Api* api() {
     BIND(device_count, "rife_b200_device_count")
     BIND(create, "rife_b200_create")
     BIND(load, "rife_b200_load")
+    BIND(load_w, "rife_b200_load_w")
+    BIND(set_option, "rife_b200_set_option")
     BIND(process, "rife_b200_process")
     BIND(last_error, "rife_b200_last_error")
     BIND(destroy, "rife_b200_destroy")
@@ -68,6 +72,9 @@ RIFE::RIFE(int gpuid, bool tta_mode, bool tta_temporal_mode, bool uhd_mode, int 
     }
     create_status = a->create(&handle, gpuid, tta_mode, tta_temporal_mode, uhd_mode, num_threads, rife_v2, rife_v4);
     if (create_status) fprintf(stderr, "rife_b200_create(gpu %d) failed: %d\n", gpuid, create_status);
+#if _WIN32
+    if (!create_status) a->set_option(handle, "bgr", 1);  // the Windows codecs of src/main.cpp produce / consume B,G,R
+#endif
 }
 
 RIFE::~RIFE()
@@ -81,6 +88,20 @@ int RIFE::load(const std::string& modeldir)
     int r = api()->load(handle, modeldir.c_str());
     if (r) fprintf(stderr, "rife_b200_load(%s) failed: %s\n", modeldir.c_str(), api()->last_error(handle));
     return r;
+}
+
+int RIFE::load(const std::wstring& modeldir)
+{
+    if (!handle) return -1;
+    int r = api()->load_w(handle, modeldir.c_str());
+    if (r) fprintf(stderr, "rife_b200_load_w failed: %s\n", api()->last_error(handle));
+    return r;
+}
+
+int RIFE::set_bgr(bool bgr)
+{
+    if (!handle) return -1;
+    return api()->set_option(handle, "bgr", bgr ? 1 : 0);
 }
 
 int RIFE::process(const ncnn::Mat& in0image, const ncnn::Mat& in1image, float timestep, ncnn::Mat& outimage) const

@@ -17,6 +17,11 @@ public:
     ~RIFE();
 
     int load(const std::string& modeldir);
+    // the reference's Windows build declares load(const std::wstring&) instead (src/rife.h:21-25) and hands over / expects
+    // B,G,R frames (src/rife.cpp:438-444, rife_preproc.comp:13,53-56): both are available here on every platform, the BGR
+    // channel order is switched on automatically under _WIN32 (or with set_bgr)
+    int load(const std::wstring& modeldir);
+    int set_bgr(bool bgr);
 
     // in0image / in1image: w x h packed RGB u8 (elemsize 3, elempack 3); outimage: caller-allocated same shape.
     // timestep 0 / 1 rebinds outimage to the input Mat, as the reference does (src/rife.cpp:3206-3216).

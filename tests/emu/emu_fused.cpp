@@ -101,14 +101,18 @@ static void ref_warp(const float* img, const float* fx, const float* fy, int h, 
 
 struct Case {
     int w, h, wp, hp, n;
+    bool v4 = false;                     // rife-v4 layout: 5 planes per block output at half the block resolution
+    int contig = 0;                      // tail: 0 = crop the padded rows, 1 = the reference CPU path's contiguous read
+    int dch() const { return v4 ? 5 : 6; }
+    int up() const { return v4 ? 2 : 1; }
     std::vector<uchar4> rgbx;            // 2 * n frames, padded
     std::vector<float> d[4];             // per block: n x 6 planes at 1/8, 1/4, 1/2, 1/1
     TBatch tb;
     InBatch ib;
 };
 
-static void make_case(Case& c, int w, int h, int n) {
-    c.w = w; c.h = h; c.n = n;
+static void make_case(Case& c, int w, int h, int n, bool v4 = false, int contig = 0) {
+    c.w = w; c.h = h; c.n = n; c.v4 = v4; c.contig = contig;
     c.wp = (w + 31) / 32 * 32; c.hp = (h + 31) / 32 * 32;
     const size_t plane = (size_t)c.wp * c.hp;
     c.rgbx.assign(2 * n * plane, make_uchar4(0, 0, 0, 0));
@@ -121,11 +125,11 @@ static void make_case(Case& c, int w, int h, int n) {
             }
     static const int S[4] = {8, 4, 2, 1};
     for (int k = 0; k < 4; k++) {
-        const size_t hk = c.hp / S[k], wk = c.wp / S[k];
-        c.d[k].resize((size_t)n * 6 * hk * wk);
+        const size_t hk = c.hp / S[k] / c.up(), wk = c.wp / S[k] / c.up();
+        c.d[k].resize((size_t)n * c.dch() * hk * wk);
         // flow increments of a few pixels at this block's own scale, mask increments of order 1
         for (size_t i = 0; i < c.d[k].size(); i++) {
-            const int ch = (int)((i / (hk * wk)) % 6);
+            const int ch = (int)((i / (hk * wk)) % c.dch());
             c.d[k][i] = ch < 4 ? frand(-1.5f, 1.5f) : frand(-2.f, 2.f);
         }
     }
@@ -154,15 +158,20 @@ static void run_fused(Case& c, int rc, Result& r) {
         dim3 g(cdiv(wk, 128), hk, n), b(128, 1, 1);
         float* d0 = c.d[0].data(); float* d1 = c.d[1].data(); float* d2 = c.d[2].data();
         __half* x = r.x[k].data();
+        const int dch = c.dch();
         if (k == 0) launch(g, b, head0_kernel, c.ib, c.tb, hp, wp, hk, wk, x);
-        else if (k == 1) launch(g, b, head_update_kernel<4, 8, 0, 8, false>, c.ib, F.data(), M.data(), (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+        else if (c.v4) {
+            if (k == 1) launch(g, b, head_update_kernel<4, 16, 0, 16, false>, c.ib, F.data(), M.data(), (const float*)d0, hp / 16, wp / 16, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
+            else if (k == 2) launch(g, b, head_update_kernel<2, 8, 1, 16, true>, c.ib, F.data(), M.data(), (const float*)d1, hp / 8, wp / 8, (const float*)d0, hp / 16, wp / 16, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
+            else launch(g, b, head_update_kernel<1, 4, 2, 16, true>, c.ib, F.data(), M.data(), (const float*)d2, hp / 4, wp / 4, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
+        } else if (k == 1) launch(g, b, head_update_kernel<4, 8, 0, 8, false>, c.ib, F.data(), M.data(), (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
         else if (k == 2) {
-            if (rc2) launch(g, b, head_update_kernel<2, 4, 1, 8, false>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
-            else launch(g, b, head_update_kernel<2, 4, 1, 8, true>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+            if (rc2) launch(g, b, head_update_kernel<2, 4, 1, 8, false>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
+            else launch(g, b, head_update_kernel<2, 4, 1, 8, true>, c.ib, F.data(), M.data(), (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
         } else {
-            if (rc2) launch(g, b, head_update_kernel<1, 2, 3, 4, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, c.tb, hp, wp, hk, wk, x);
-            else if (rc1) launch(g, b, head_update_kernel<1, 2, 2, 8, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
-            else launch(g, b, head_update_kernel<1, 2, 2, 8, true>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x);
+            if (rc2) launch(g, b, head_update_kernel<1, 2, 3, 4, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)d1, hp / 4, wp / 4, (const float*)d0, hp / 8, wp / 8, c.tb, hp, wp, hk, wk, x, dch);
+            else if (rc1) launch(g, b, head_update_kernel<1, 2, 2, 8, false>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
+            else launch(g, b, head_update_kernel<1, 2, 2, 8, true>, c.ib, F.data(), M.data(), (const float*)d2, hp / 2, wp / 2, (const float*)nullptr, 0, 0, (const float*)nullptr, 0, 0, c.tb, hp, wp, hk, wk, x, dch);
         }
     }
     r.out.assign((size_t)n * c.w * c.h * 3, 0);
@@ -171,9 +180,11 @@ static void run_fused(Case& c, int rc, Result& r) {
     DSrc ds;
     ds.d[0] = c.d[0].data(); ds.d[1] = c.d[1].data(); ds.d[2] = c.d[2].data();
     dim3 tg(cdiv(c.w, 128), c.h, n), tbk(128, 1, 1);
-    if (rc2) launch(tg, tbk, tail_kernel<2>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
-    else if (rc1) launch(tg, tbk, tail_kernel<1>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
-    else launch(tg, tbk, tail_kernel<0>, c.ib, (const float*)F.data(), (const float*)M.data(), (const float*)c.d[3].data(), hp, wp, ob, c.w, c.h, ds);
+    const float* Fc = F.data(); const float* Mc = M.data(); const float* d3 = c.d[3].data();
+    if (c.v4) launch(tg, tbk, tail_kernel<0, 2>, c.ib, Fc, Mc, d3, hp, wp, ob, c.w, c.h, ds, c.contig, c.dch(), 0);
+    else if (rc2) launch(tg, tbk, tail_kernel<2, 1>, c.ib, Fc, Mc, d3, hp, wp, ob, c.w, c.h, ds, c.contig, c.dch(), 0);
+    else if (rc1) launch(tg, tbk, tail_kernel<1, 1>, c.ib, Fc, Mc, d3, hp, wp, ob, c.w, c.h, ds, c.contig, c.dch(), 0);
+    else launch(tg, tbk, tail_kernel<0, 1>, c.ib, Fc, Mc, d3, hp, wp, ob, c.w, c.h, ds, c.contig, c.dch(), 0);
 }
 
 // value of channel ch of head tensor k (C8 space-to-depth, hi + lo planes) at output pixel (oy, ox)
@@ -214,8 +225,8 @@ static void run_reference(const Case& c, int b, std::vector<float> xr[4], std::v
             ref_resize(T.data(), hp, wp, &xr[0][6 * pk], hk, wk);
         } else {
             // update after block k-1
-            const int sp = S[k - 1], dh = hp / sp, dw = wp / sp;
-            const float* d = c.d[k - 1].data() + (size_t)b * 6 * dh * dw;
+            const int sp = S[k - 1] * c.up(), dh = hp / sp, dw = wp / sp;  // v4: 5 planes at half the block resolution, factor 2*S
+            const float* d = c.d[k - 1].data() + (size_t)b * c.dch() * dh * dw;
             for (int ch = 0; ch < 5; ch++) {
                 ref_resize(d + (size_t)ch * dh * dw, dh, dw, tmp.data(), hp, wp);
                 for (size_t i = 0; i < plane; i++) {
@@ -240,9 +251,21 @@ static void run_reference(const Case& c, int b, std::vector<float> xr[4], std::v
         }
     }
     // final update + blend + quantise (flownet.param:202-217, rife.cpp:4375-4398)
-    const float* d3 = c.d[3].data() + (size_t)b * 6 * plane;
-    for (int ch = 0; ch < 4; ch++) for (size_t i = 0; i < plane; i++) F[ch][i] = F[ch][i] + d3[ch * plane + i];
-    for (size_t i = 0; i < plane; i++) M[i] = M[i] + d3[4 * plane + i];
+    if (!c.v4) {
+        const float* d3 = c.d[3].data() + (size_t)b * 6 * plane;
+        for (int ch = 0; ch < 4; ch++) for (size_t i = 0; i < plane; i++) F[ch][i] = F[ch][i] + d3[ch * plane + i];
+        for (size_t i = 0; i < plane; i++) M[i] = M[i] + d3[4 * plane + i];
+    } else {  // rife-v4: U = bilinear(flow3, 2); F = F*1 + U*2 (Eltwise), M = M + U[4]  (models/rife-v4/flownet.param:152-160)
+        const int dh = hp / 2, dw = wp / 2;
+        const float* d3 = c.d[3].data() + (size_t)b * 5 * dh * dw;
+        for (int ch = 0; ch < 5; ch++) {
+            ref_resize(d3 + (size_t)ch * dh * dw, dh, dw, tmp.data(), hp, wp);
+            for (size_t i = 0; i < plane; i++) {
+                if (ch < 4) F[ch][i] = F[ch][i] * 1.f + tmp[i] * 2.f;
+                else M[i] = M[i] + tmp[i];
+            }
+        }
+    }
     std::vector<float> O[3];
     for (int ch = 0; ch < 3; ch++) {
         std::vector<float> w0(plane), w1(plane);
@@ -257,10 +280,14 @@ static void run_reference(const Case& c, int b, std::vector<float> xr[4], std::v
         }
     }
     out.resize((size_t)c.w * c.h * 3);
-    for (size_t i = 0; i < (size_t)c.w * c.h; i++)  // contiguous read of the padded planes (rife.cpp:4375-4387)
-        for (int ch = 0; ch < 3; ch++) {
-            int iv = (int)(O[ch][i] * 255.f + 0.5f);
-            out[i * 3 + ch] = (uint8_t)std::min(std::max(iv, 0), 255);
+    for (int y = 0; y < c.h; y++)
+        for (int x = 0; x < c.w; x++) {
+            // crop of the padded planes (rife_postproc.comp:42), or the reference CPU path's contiguous read (rife.cpp:4375-4387)
+            const size_t i = (size_t)y * c.w + x, src = c.contig ? i : (size_t)y * wp + x;
+            for (int ch = 0; ch < 3; ch++) {
+                int iv = (int)(O[ch][src] * 255.f + 0.5f);
+                out[i * 3 + ch] = (uint8_t)std::min(std::max(iv, 0), 255);
+            }
         }
 }
 
@@ -290,14 +317,15 @@ int main(int argc, char** argv) {
         printf("lin_coeff (RIFE_FUSED_LEAN=%d) vs reference arithmetic: %ld mismatches\n", RIFE_FUSED_LEAN, bad);
         if (bad) fails++;
     }
-    const int sizes[][3] = {{64, 64, 2}, {100, 70, 3}, {160, 96, 1}, {96, 128, 2}};
+    // {w, h, pairs, rife-v4 layout, contiguous-read quirk}
+    const int sizes[][5] = {{64, 64, 2, 0, 0}, {100, 70, 3, 0, 0}, {100, 70, 2, 0, 1}, {160, 96, 1, 0, 0}, {96, 128, 2, 0, 0}, {64, 64, 2, 1, 0}, {100, 70, 2, 1, 0}, {100, 70, 1, 1, 1}};
     for (auto& sz : sizes) {
         Case c;
-        make_case(c, sz[0], sz[1], sz[2]);
+        make_case(c, sz[0], sz[1], sz[2], sz[3] != 0, sz[4]);
         Result r0, r1, r2;
         run_fused(c, 0, r0);
-        run_fused(c, 1, r1);
-        run_fused(c, 2, r2);
+        run_fused(c, c.v4 ? 0 : 1, r1);  // the recompute variants exist for the v4.6 layout only
+        run_fused(c, c.v4 ? 0 : 2, r2);
         static const int S[4] = {8, 4, 2, 1};
         for (int k = 0; k < 4; k++) {
             const size_t nb = r0.x[k].size() * sizeof(__half);
@@ -334,7 +362,7 @@ int main(int argc, char** argv) {
         }
         for (int k = 0; k < 4; k++) sum = fnv(sum, r0.x[k].data(), r0.x[k].size() * sizeof(__half));
         sum = fnv(sum, r0.out.data(), r0.out.size());
-        printf("%dx%d n=%d: head tensors vs restatement max rel err %.3g, output bytes differing %zu (max %zu)\n", sz[0], sz[1], sz[2], worst, odiff, omax);
+        printf("%dx%d n=%d%s%s: head tensors vs restatement max rel err %.3g, output bytes differing %zu (max %zu)\n", sz[0], sz[1], sz[2], c.v4 ? " v4" : "", c.contig ? " contig" : "", worst, odiff, omax);
         if (worst > 2e-6) { printf("FAIL %dx%d: head tensor mismatch\n", sz[0], sz[1]); fails++; }
         if (omax > 0) { printf("FAIL %dx%d: output mismatch\n", sz[0], sz[1]); fails++; }
     }

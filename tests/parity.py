@@ -66,9 +66,14 @@ def port_binary():
     return p if os.path.exists(p) else None
 
 
-def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd=False, threads=None, repeat=1, warmup=0, which="auto", modeldir=None):
+def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd=False, threads=None, repeat=1, warmup=0, which="auto", modeldir=None,
+               crop_padded=False):
     """Returns (out u8 array, info dict).  which: 'ref' | 'port' | 'auto' (ref if present else port).
-    modeldir overrides the lookup of `model` (the family flags still come from the name)."""
+    modeldir overrides the lookup of `model` (the family flags still come from the name).
+    crop_padded (port only): crop the padded output rows like the reference's GPU path instead of reproducing the CPU path's
+    contiguous read (src/rife.cpp:4375-4387); the two differ only when w % 32 != 0 and no spatial TTA is used."""
+    if crop_padded:
+        which = "port"
     exe = None
     kind = None
     if which in ("auto", "ref"):
@@ -89,6 +94,8 @@ def run_oracle(model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, uhd
         np.ascontiguousarray(in1).tofile(b)
         cmd = [exe, "--model", md, "--family", FAMILY[model], "--w", str(w), "--h", str(h), "--in0", a, "--in1", b, "--out", o,
                "--t", repr(float(timestep)), "--repeat", str(repeat), "--warmup", str(warmup)]
+        if crop_padded:
+            cmd.append("--crop-padded")
         if tta:
             cmd.append("--tta")
         if tta_temporal:
@@ -125,9 +132,18 @@ def run_gpu(pkg, model, in0, in1, timestep=0.5, tta=False, tta_temporal=False, u
         r.close()
 
 
-def check_case(pkg, model="rife-v4.6", w=256, h=192, timestep=0.5, tta=False, tta_temporal=False, uhd=False, dx=3, dy=2, seed=0, options=None):
+def check_case(pkg, model="rife-v4.6", w=256, h=192, timestep=0.5, tta=False, tta_temporal=False, uhd=False, dx=3, dy=2, seed=0, options=None, crop="reference"):
+    """crop (matters only when w % 32 != 0 and no spatial TTA): "reference" compares with the reference's own CPU path, whose
+    contiguous read of the padded output the library reproduces under option cpu_crop_quirk = 1; "padded" compares the
+    library's default (the crop of the padded rows, as the reference's GPU path does) with the restatement run with --crop-padded."""
     in0, in1 = synth.pair(w, h, dx=dx, dy=dy, seed=seed)
-    ref, info = run_oracle(model, in0, in1, timestep, tta, tta_temporal, uhd)
+    options = dict(options or {})
+    if crop == "reference":
+        if w % 32 and not tta:
+            options["cpu_crop_quirk"] = 1
+        ref, info = run_oracle(model, in0, in1, timestep, tta, tta_temporal, uhd)
+    else:
+        ref, info = run_oracle(model, in0, in1, timestep, tta, tta_temporal, uhd, crop_padded=True)
     out = run_gpu(pkg, model, in0, in1, timestep, tta, tta_temporal, uhd, options=options)
     res = compare(out, ref)
     res["oracle"] = info["kind"]

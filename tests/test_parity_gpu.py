@@ -85,7 +85,9 @@ def test_golden_frames(pkg):
             continue
         a, b = parity.synth.pair(m["w"], m["h"], **m["synth_kwargs"])
         kw = dict(m["oracle_kwargs"])
-        out = parity.run_gpu(pkg, m["model"], a, b, kw.pop("timestep", 0.5), kw.get("tta", False), kw.get("tta_temporal", False), kw.get("uhd", False))
+        # the goldens are outputs of the reference's CPU path: ragged widths carry its contiguous-read quirk (rife.cpp:4375-4387)
+        opts = {"cpu_crop_quirk": 1} if m["w"] % 32 and not kw.get("tta", False) else None
+        out = parity.run_gpu(pkg, m["model"], a, b, kw.pop("timestep", 0.5), kw.get("tta", False), kw.get("tta_temporal", False), kw.get("uhd", False), options=opts)
         res = parity.compare(out, arrays[name])
         assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, (name, res)
         checked += 1
@@ -130,7 +132,7 @@ def test_v46_fused_fast_path(pkg, w, h):
     r.close()
     d = parity.compare(fast, generic)
     assert d["max_abs_diff"] <= 1 and d["share_ne"] < 5e-3, d
-    if w * h <= 640 * 360:
+    if w % 32 == 0:  # ragged widths: see test_ragged_widths_crop_the_padded_output
         ref, _ = parity.run_oracle("rife-v4.6", a, b, 0.5)
         res = parity.compare(fast, ref)
         assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
@@ -219,8 +221,8 @@ def test_batched_lockstep_equals_single_pair_path(pkg):
 def test_v46_recompute_fm_modes_are_bit_identical(pkg, w, h):
     """recompute_fm 1 / 2: the full-resolution flow / mask planes are rebuilt from the per-block flow tensors instead of
     being stored and re-read (fused_v46.cu).  Same operations in the same order, so the frames must be identical -- for a
-    single pair, for a lock-step batch with different timesteps, and for a ragged size (w % 32 != 0: the tail's
-    contiguous-read quirk of src/rife.cpp:4375-4387)."""
+    single pair, for a lock-step batch with different timesteps, and for a ragged size (w % 32 != 0), there with and without
+    the contiguous-read quirk of src/rife.cpp:4375-4387."""
     _need("rife-v4.6")
     nb = 3 if w * h > 1000000 else 8
     frames = [parity.synth.frame(k, w, h, dx=5, dy=3) for k in range(nb + 1)]
@@ -231,6 +233,7 @@ def test_v46_recompute_fm_modes_are_bit_identical(pkg, w, h):
     assert r.get_option("fast_active") == 1
     r.set_option("lanes", 1)
     r.set_option("batch", nb)
+    r.set_option("cpu_crop_quirk", 1 if (w, h) == (100, 70) else 0)
     results = {}
     for mode in (0, 1, 2):
         r.set_option("recompute_fm", mode)
@@ -284,3 +287,208 @@ def test_concurrent_process_calls_are_combined_into_batches(pkg):
     for e, g_ in zip(expect, got):
         assert np.array_equal(e, g_)
     assert nr == 32 and nb < nr, (nb, nr)
+
+
+# ---- round 2: the resolutions the metric is quoted on, the other model directories, the boundary options ------------------------
+
+def _batch_vs_oracle(pkg, model, w, h, ts, lanes=2, threads=None):
+    """len(ts) consecutive pairs of the synthetic stream through ONE process_batch call (lock-step batches on the fused path),
+    each pair with its own timestep, every output compared with the oracle's frame for that pair."""
+    n = len(ts)
+    frames = [parity.synth.frame(k, w, h) for k in range(n + 1)]
+    v2, v4 = pkg.family_flags(model)
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir(model))
+    r.set_option("lanes", lanes)
+    fast = r.get_option("fast_active")
+    outs = [np.empty_like(frames[0]) for _ in range(n)]
+    r.process_batch_ptr([f.ctypes.data for f in frames[:n]], [f.ctypes.data for f in frames[1:]], w, h, ts, [o.ctypes.data for o in outs])
+    r.close()
+    worst = None
+    for i in range(n):
+        ref, info = parity.run_oracle(model, frames[i], frames[i + 1], ts[i], threads=threads)
+        res = parity.compare(outs[i], ref)
+        assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, (model, w, h, i, ts[i], res)
+        assert outs[i].std() > 5
+        if worst is None or res["psnr_db"] < worst["psnr_db"]:
+            worst = res
+    return fast, worst
+
+
+def test_v46_1080p_lockstep_batch_vs_oracle(pkg):
+    """BASELINE configs[1] at its own resolution: 8 pairs of 1920x1080 in one lock-step batch, distinct timesteps, vs the oracle."""
+    _need("rife-v4.6")
+    fast, worst = _batch_vs_oracle(pkg, "rife-v4.6", 1920, 1080, [0.5, 0.25, 0.75, 0.5, 0.125, 0.625, 0.5, 0.875])
+    assert fast == 1
+    print("1080p worst pair:", worst)
+
+
+def test_v46_4k_lockstep_batch_vs_oracle(pkg):
+    """BASELINE configs[2] at its own resolution: 3840x2160 (padded to 3840x2176), two pairs per lock-step batch, vs the oracle."""
+    _need("rife-v4.6")
+    fast, worst = _batch_vs_oracle(pkg, "rife-v4.6", 3840, 2160, [0.5, 0.25])
+    assert fast == 1
+    print("4K worst pair:", worst)
+
+
+def test_v4_1080p_timestep_sweep_vs_oracle(pkg):
+    """BASELINE configs[4]: rife-v4, the -n 4x schedule t = 0.25, 0.5, 0.75 at 1080p, on the fused path of the rife-v4 layout."""
+    _need("rife-v4")
+    fast, worst = _batch_vs_oracle(pkg, "rife-v4", 1920, 1080, [0.25, 0.5, 0.75])
+    assert fast == 1
+    print("rife-v4 1080p worst pair:", worst)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (640, 360), (100, 70)])
+def test_v4_fused_path_matches_generic_executor(pkg, w, h):
+    """The hand-scheduled path of the rife-v4 layout (PReLU, one residual per chain, 5-channel flow heads at half the block
+    resolution): active after the load-time self-check, equal to the generic executor up to fp32 rounding, within tolerance
+    of the oracle."""
+    _need("rife-v4")
+    a, b = parity.synth.pair(w, h)
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    r.load(parity.model_dir("rife-v4"))
+    assert r.get_option("fast_active") == 1
+    fast = r.process(a, b, 0.3)
+    r.set_option("fast", 0)
+    generic = r.process(a, b, 0.3)
+    r.close()
+    d = parity.compare(fast, generic)
+    assert d["max_abs_diff"] <= 1 and d["share_ne"] < 5e-3, d
+    if w % 32 == 0:
+        ref, _ = parity.run_oracle("rife-v4", a, b, 0.3)
+        res = parity.compare(fast, ref)
+        assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
+
+
+ALL_MODELS = ["rife", "rife-HD", "rife-UHD", "rife-anime", "rife-v2", "rife-v2.3", "rife-v2.4", "rife-v3.0", "rife-v3.1", "rife-v4", "rife-v4.6"]
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_every_model_directory_vs_oracle(pkg, model):
+    """every model directory the reference ships (src/main.cpp:658-683 sniffs them all), default
+    precision tier, against the oracle."""
+    _need(model)
+    t = 0.5 if parity.FAMILY[model] != "v4" else 0.4
+    _ok(parity.check_case(pkg, model, 256, 192, timestep=t))
+
+
+@pytest.mark.parametrize("model,uhd", [("rife-UHD", True), ("rife-v3.1", True), ("rife-HD", False)])
+def test_more_models_with_tta(pkg, model, uhd):
+    _need(model)
+    _ok(parity.check_case(pkg, model, 160, 96, tta=True, tta_temporal=True, uhd=uhd))
+
+
+@pytest.mark.parametrize("model,fast", [("rife-v4.6", 1), ("rife-v4.6", 0), ("rife-v4", 1), ("rife-v2.3", 0)])
+@pytest.mark.parametrize("w,h", [(100, 70), (90, 50)])
+def test_ragged_widths_crop_the_padded_output(pkg, model, fast, w, h):
+    """w % 32 != 0.  Default: the frame is the crop of the padded result (what the reference's GPU path produces,
+    rife_postproc.comp:42) -- checked against the restatement run with --crop-padded AND through a size-independent property:
+    it must equal the crop of the result for the same frames zero-padded to the padded size by the caller (same arithmetic,
+    bit for bit).  Option cpu_crop_quirk = 1: the reference CPU path's sheared frame (rife.cpp:4375-4387), checked against the
+    reference binary itself."""
+    _need(model)
+    a, b = parity.synth.pair(w, h)
+    opts = {"fast": fast}
+    v2, v4 = pkg.family_flags(model)
+    t = 0.5
+    r = pkg.RIFE(0, False, False, False, 1, v2, v4)
+    r.load(parity.model_dir(model))
+    r.set_option("fast", fast)
+    out = r.process(a, b, t)
+    wp, hp = (w + 31) // 32 * 32, (h + 31) // 32 * 32
+    ap, bp = np.zeros((hp, wp, 3), np.uint8), np.zeros((hp, wp, 3), np.uint8)
+    ap[:h, :w], bp[:h, :w] = a, b
+    full = r.process(ap, bp, t)
+    r.set_option("cpu_crop_quirk", 1)
+    quirk = r.process(a, b, t)
+    r.close()
+    assert np.array_equal(out, full[:h, :w])
+    res = parity.compare(out, parity.run_oracle(model, a, b, t, crop_padded=True)[0])
+    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
+    res = parity.compare(quirk, parity.run_oracle(model, a, b, t)[0])
+    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, res
+    assert not np.array_equal(out, quirk)
+    del opts
+
+
+@pytest.mark.parametrize("model,tta", [("rife-v4.6", False), ("rife-v4.6", True), ("rife-v2.3", False)])
+def test_bgr_frames(pkg, model, tta):
+    """Option "bgr" (the reference's Windows build hands over B,G,R frames, rife_preproc.comp:13,53-56): processing the
+    channel-swapped frames with the option on must give the channel-swapped result, bit for bit."""
+    _need(model)
+    a, b = parity.synth.pair(160, 96)
+    v2, v4 = pkg.family_flags(model)
+    r = pkg.RIFE(0, tta, False, False, 1, v2, v4)
+    r.load(parity.model_dir(model))
+    rgb = r.process(a, b, 0.5)
+    r.set_option("bgr", 1)
+    bgr = r.process(np.ascontiguousarray(a[:, :, ::-1]), np.ascontiguousarray(b[:, :, ::-1]), 0.5)
+    r.close()
+    assert np.array_equal(bgr[:, :, ::-1], rgb)
+
+
+def test_frame_cache_reuses_uploads_across_calls(pkg):
+    """Option "frame_cache" (SURVEY.md 8f, N1): frame k+1 of pair (k, k+1) is found on the device when pair (k+1, k+2) arrives."""
+    _need("rife-v4.6")
+    w, h = 320, 192
+    frames = [parity.synth.frame(k, w, h) for k in range(6)]
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    r.load(parity.model_dir("rife-v4.6"))
+    expect = [r.process(frames[i], frames[i + 1], 0.5) for i in range(5)]
+    assert r.get_option("frame_cache_hits") == 0
+    h2d0 = pkg.copy_bytes()[0]
+    r.set_option("frame_cache", 1)
+    got = [r.process(frames[i], frames[i + 1], 0.5) for i in range(5)]
+    hits = r.get_option("frame_cache_hits")
+    h2d = pkg.copy_bytes()[0] - h2d0
+    # a buffer whose content changed must be announced
+    frames[5][:] = frames[0]
+    r.forget_frames()
+    again = r.process(frames[4], frames[5], 0.5)
+    fresh = pkg.RIFE(0, False, False, False, 1, False, True)
+    fresh.load(parity.model_dir("rife-v4.6"))
+    want = fresh.process(frames[4], frames[5], 0.5)
+    fresh.close()
+    r.close()
+    for e, g_ in zip(expect, got):
+        assert np.array_equal(e, g_)
+    assert hits == 4 and h2d == 6 * w * h * 3, (hits, h2d)
+    assert np.array_equal(again, want)
+
+
+def test_failed_reload_leaves_the_engine_usable(pkg):
+    """load_packed with a damaged blob on a loaded engine must fail without touching the loaded model (transactional load)."""
+    _need("rife-v4.6")
+    a, b = parity.synth.pair(256, 160)
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    r.load(parity.model_dir("rife-v4.6"))
+    before = r.process(a, b, 0.5)
+    blob = r.export_weights().copy()
+    bad = blob[: len(blob) // 2]
+    with pytest.raises(pkg.RifeError):
+        r.load_packed(bad)
+    bad2 = blob.copy()
+    bad2[12:20] = 255  # param length = 2^64 - 1: must be rejected, not wrapped around
+    with pytest.raises(pkg.RifeError):
+        r.load_packed(bad2)
+    assert r.get_option("fast_active") == 1
+    assert np.array_equal(r.process(a, b, 0.5), before)
+    r.load_packed(blob)
+    assert np.array_equal(r.process(a, b, 0.5), before)
+    r.close()
+
+
+def test_null_frame_in_a_batch_is_rejected_before_anything_is_queued(pkg):
+    _need("rife-v4.6")
+    w, h = 128, 96
+    frames = [parity.synth.frame(k, w, h) for k in range(4)]
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    r.load(parity.model_dir("rife-v4.6"))
+    outs = [np.full_like(frames[0], 7) for _ in range(3)]
+    with pytest.raises(pkg.RifeError):
+        r.process_batch_ptr([frames[0].ctypes.data, frames[1].ctypes.data, None], [f.ctypes.data for f in frames[1:]], w, h, [0.5] * 3, [o.ctypes.data for o in outs])
+    assert all((o == 7).all() for o in outs)  # nothing was written
+    ok = r.process(frames[0], frames[1], 0.5)
+    r.close()
+    assert ok.std() > 5
