@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librife_b200.so")
+# RIFE_B200_LIB: an alternative build of the same library (A/B timing of compile-time switches); the default is the in-tree build
+LIB_PATH = os.environ.get("RIFE_B200_LIB") or os.path.join(_HERE, "lib", "librife_b200.so")
 
 ERRORS = {0: "ok", -1: "bad argument", -2: "CUDA device error", -3: "model error", -4: "process before load", -5: "internal error"}
 
