@@ -248,6 +248,11 @@ int Engine::set_option(const std::string& key, int value) {
         if (!frame_cache_) for (auto& f : frames_) f.host = nullptr;
         return 0;
     }
+    if (key == "head_pack") {  // fused path: packed block-head tensors (32 instead of 64 bytes per pixel; fused_v46_kernels.cuh)
+        head_pack_ = value != 0;
+        for (Lane* L : lanes_) if (L->fast) L->fast->set_head_pack(head_pack_);
+        return 0;
+    }
     if (key == "ktime") {  // per-stage event times on the fused path (stage_report); lanes no longer overlap while it is on
         cudaDeviceSynchronize();
         for (Lane* L : lanes_) if (L->fast) L->fast->set_ktime(value);
@@ -284,6 +289,7 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "recompute_fm") *value = recompute_fm_;
     else if (key == "combine") *value = combine_;
     else if (key == "cpu_crop_quirk") *value = cpu_crop_quirk_;
+    else if (key == "head_pack") *value = head_pack_;
     else if (key == "bgr") *value = bgr_;
     else if (key == "frame_cache") *value = frame_cache_;
     else if (key == "frame_cache_hits") *value = (int)frame_hits_;
@@ -307,6 +313,7 @@ void Engine::setup_fast() {
         L->fast->set_recompute(recompute_fm_);
         L->fast->set_crop_quirk(cpu_crop_quirk_);
         L->fast->set_bgr(bgr_);
+        L->fast->set_head_pack(head_pack_);
         if (L->fast->init(nets_[0].get(), lanes_[0]->run[0], err)) {
             for (Lane* L2 : lanes_) { delete L2->fast; L2->fast = nullptr; }
             return;

@@ -42,6 +42,7 @@ struct Lane {
 };
 
 constexpr int RECOMPUTE_FM_DEFAULT = 0;
+constexpr int HEAD_PACK_DEFAULT = 0;
 constexpr int COMBINE_DEFAULT = 1;  // measured (profiles/r1_s21/process_threads_1080p.txt): 8 caller threads 668 -> 1091 process() calls/s at 1080p
 
 class Engine {
@@ -92,6 +93,7 @@ private:
     int plain_mask_ = 12;  // IFBlocks 2 and 3 (80 % of the FLOPs): plain fp16 activations in the residual chain (profiles/r1_precision_study_plain_blocks.txt)
     int combine_ = COMBINE_DEFAULT;  // concurrent process() calls on this handle are executed as one lock-step batch (combiner.h)
     int cpu_crop_quirk_ = 0;  // 1: reproduce the reference CPU path's contiguous read of the padded output (rife.cpp:4375-4387)
+    int head_pack_ = HEAD_PACK_DEFAULT;  // fused path: packed block-head tensors (fused_v46_kernels.cuh)
     int bgr_ = 0;             // frames are B,G,R in memory (the reference's Windows build: rife_preproc.comp:13,53-56)
     Combiner<HostReq> combiner_;
     int run_combined(HostReq** rq, int n);

@@ -166,12 +166,29 @@ int V46Runner::init(const Net* net, const NetRunner* weights, std::string& err) 
         }
     }
     if (net->find_blob("flow3") < 0 || net->find_blob("out0") < 0) { err = "no flow3 / out0 in graph"; return -1; }
+    // option "head_pack": the first stride-2 conv of blocks 1-3 reads a 16-slot tensor whose slots 12..15 carry the lo parts
+    // of the flow channels 8..11 -- its weights for those slots are copies of the flow channels' weights
+    for (int k = 0; k < 4; k++) {
+        if (wpk_head_[k]) { cudaFree(wpk_head_[k]); wpk_head_[k] = nullptr; }
+        if (k == 0) continue;  // 7 channels, no flow input: the plain hi plane is all there is
+        const Layer& L = net->layers[cfg_[k * 11].layer];
+        const int cout = L.geti(0, 0), cin = 12;
+        std::vector<float> w16((size_t)cout * 16 * 9, 0.f);
+        for (int oc = 0; oc < cout; oc++)
+            for (int ic = 0; ic < 16; ic++)
+                for (int t = 0; t < 9; t++) w16[((size_t)oc * 16 + ic) * 9 + t] = L.weight[((size_t)oc * cin + (ic < 12 ? ic : ic - 4)) * 9 + t];
+        std::vector<uint16_t> pk;
+        pack_conv3x3s2_weights(w16.data(), cout, 16, 16, weights->weights(cfg_[k * 11].layer).tcN, pk);
+        if (cudaMalloc(&wpk_head_[k], pk.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -2; }
+        cudaMemcpy(wpk_head_[k], pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
+    }
     ok_ = true;
     return 0;
 }
 
 V46Runner::~V46Runner() {
     for (void* p : bufs_) cudaFree(p);
+    for (auto& p : wpk_head_) cudaFree(p);
     delete tm_;
 }
 
@@ -227,6 +244,7 @@ int V46Runner::conv(int slot, const __half* in, __half* out, const __half* res, 
     TcConvArgs a;
     memset(&a, 0, sizeof a);
     a.wpk = (const __half*)W.wpk;
+    if (head_pack_ && slot % 11 == 0 && wpk_head_[slot / 11]) a.wpk = wpk_head_[slot / 11];  // flow channels seen twice (hi + lo slots)
     a.bias = W.biasN;
     a.H = oh; a.W = ow; a.Cin = W.cinp; a.Cout = L.geti(0, 0); a.N = W.tcN;
     a.split_in = split_in;
@@ -312,20 +330,20 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         const int hk = hp / S[k], wk = wp / S[k];
         dim3 g(cdiv(wk, 128), hk, n);
         // head of block k, fused with the flow / mask update that follows block k-1
-        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(ib, tb, hp, wp, hk, wk, x_[0]);
+        if (k == 0) head0_kernel<<<g, 128, 0, st>>>(ib, tb, hp, wp, hk, wk, x_[0], head_pack_);
         else if (v4_) {
             // rife-v4: d_{k-1} has 5 planes at 1/(2*S_{k-1}) of the frame, so the up-sampling factors double
-            if (k == 1) head_update_kernel<4, 16, 0, 16, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 16, wp / 16, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[1], dch);
-            else if (k == 2) head_update_kernel<2, 8, 1, 16, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 8, wp / 8, d_[0], hp / 16, wp / 16, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch);
-            else head_update_kernel<1, 4, 2, 16, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 4, wp / 4, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch);
-        } else if (k == 1) head_update_kernel<4, 8, 0, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 8, wp / 8, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[1], dch);
+            if (k == 1) head_update_kernel<4, 16, 0, 16, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 16, wp / 16, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[1], dch, head_pack_);
+            else if (k == 2) head_update_kernel<2, 8, 1, 16, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 8, wp / 8, d_[0], hp / 16, wp / 16, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch, head_pack_);
+            else head_update_kernel<1, 4, 2, 16, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 4, wp / 4, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch, head_pack_);
+        } else if (k == 1) head_update_kernel<4, 8, 0, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[0], hp / 8, wp / 8, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[1], dch, head_pack_);
         else if (k == 2) {
-            if (rc2) head_update_kernel<2, 4, 1, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch);
-            else head_update_kernel<2, 4, 1, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch);
+            if (rc2) head_update_kernel<2, 4, 1, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch, head_pack_);
+            else head_update_kernel<2, 4, 1, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[2], dch, head_pack_);
         } else {
-            if (rc2) head_update_kernel<1, 2, 3, 4, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[3], dch);
-            else if (rc1) head_update_kernel<1, 2, 2, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch);
-            else head_update_kernel<1, 2, 2, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch);
+            if (rc2) head_update_kernel<1, 2, 3, 4, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, d_[1], hp / 4, wp / 4, d_[0], hp / 8, wp / 8, tb, hp, wp, hk, wk, x_[3], dch, head_pack_);
+            else if (rc1) head_update_kernel<1, 2, 2, 8, false><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch, head_pack_);
+            else head_update_kernel<1, 2, 2, 8, true><<<g, 128, 0, st>>>(ib, F_, M_, d_[2], hp / 2, wp / 2, nullptr, 0, 0, nullptr, 0, 0, tb, hp, wp, hk, wk, x_[3], dch, head_pack_);
         }
         g_launch_count++;
         snprintf(nm, sizeof nm, "b%d head", k); tm.mark(nm, st);
@@ -336,7 +354,7 @@ int V46Runner::run_batch(int n, const uint8_t* const* d_in0, const uint8_t* cons
         // unless the block is listed in plain_mask_ (plain fp16 activations there)
         const bool sp = !((plain_mask_ >> k) & 1);
         const bool hsp = !((plain_mask_ >> (4 + k)) & 1);  // experimental: read only the hi plane of the head tensor
-        int r = conv(L0, x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, hsp, true, st);    // 3x3 s2 + activation
+        int r = conv(L0, x_[k], y0_[k], nullptr, nullptr, hk / 2, wk / 2, true, n, hsp && !head_pack_, true, st);    // 3x3 s2 + activation
         snprintf(nm, sizeof nm, "b%d conv0", k); tm.mark(nm, st);
         __half* y1 = v4_ ? c_[k] : a_[k];
         r |= conv(L0 + 1, y0_[k], y1, nullptr, nullptr, hk / 4, wk / 4, false, n, true, sp, st);         // 3x3 s2 + activation

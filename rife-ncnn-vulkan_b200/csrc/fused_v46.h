@@ -29,6 +29,8 @@ public:
     void set_recompute(int m) { recompute_ = m < 0 ? 0 : (m > 2 ? 2 : m); }
     // 1: reproduce the reference CPU path's contiguous read of the padded output (src/rife.cpp:4375-4387) instead of cropping
     void set_crop_quirk(int q) { crop_quirk_ = q != 0; }
+    // 1: block-head tensors in the packed form (one fp16 plane; only the flow channels keep a lo part): fused_v46_kernels.cuh
+    void set_head_pack(int p) { head_pack_ = p != 0; }
     void set_bgr(int b) { bgr_ = b != 0; }  // frames are B,G,R in memory (the reference's Windows build)
     bool is_v4() const { return v4_; }
     // per-stage CUDA-event times of run_batch (diagnostics / bench.py's breakdown; synchronises the stream after every batch)
@@ -52,7 +54,8 @@ private:
     };
     ConvCfg cfg_[44];
     bool v4_ = false;                // rife-v4 layout: 5-channel flow heads at half the block resolution, PReLU, one residual per chain
-    int crop_quirk_ = 0, bgr_ = 0;
+    int crop_quirk_ = 0, bgr_ = 0, head_pack_ = 0;
+    __half* wpk_head_[4] = {};
     StageTimer* tm_ = nullptr;
     const Net* net_ = nullptr;
     const NetRunner* wr_ = nullptr;

@@ -147,6 +147,34 @@ __device__ __forceinline__ void store_c8_s2d_16(__half* out, const float* v, int
     }
 }
 
+// Packed form of the same tensor (option "head_pack"): ONE fp16 plane of 16 channel slots per pixel -- slots 0..11 = the 12
+// head channels rounded to fp16, slots 12..15 = the fp16 remainders (lo parts) of the four flow channels 8..11, whose
+// weights the consuming convolution sees twice.  The flow (hundreds of pixels with sub-pixel precision) keeps its split
+// hi+lo representation, the warped frames, timestep and mask (values of order 1 going into a conv) are plain fp16: 32 bytes
+// per pixel instead of 64, and half the tensor-core work in the stride-2 conv that reads it.
+__device__ __forceinline__ void store_c8_s2d_packed(__half* out, const float* v, int oy, int ox, int oh, int ow) {
+    const size_t sub = (size_t)(oh >> 1) * (ow >> 1);
+    const int par = (oy & 1) * 2 + (ox & 1);
+    const size_t pix = (size_t)(oy >> 1) * (ow >> 1) + (ox >> 1);
+    uint32_t g0[4], g1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        g0[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float a = v[8 + 2 * k], b = v[8 + 2 * k + 1];
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        g1[k] = *reinterpret_cast<const uint32_t*>(&h);
+        g1[2 + k] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(out + (((size_t)par * 2 + 0) * sub + pix) * 8) = make_uint4(g0[0], g0[1], g0[2], g0[3]);
+    *reinterpret_cast<uint4*>(out + (((size_t)par * 2 + 1) * sub + pix) * 8) = make_uint4(g1[0], g1[1], g1[2], g1[3]);
+}
+
 // x0 = Interp(cat(I0, I1, T), 1/8): flownet.param:9-10
 // Per-image kernel arguments are passed as __grid_constant__ structs: indexing them with blockIdx.z then reads the
 // constant bank directly (a plain by-value struct is first copied to local memory, ~20 stores per thread).
@@ -193,7 +221,7 @@ __global__ void rgbx4_kernel(const __grid_constant__ SrcBatch sb, int w, int h, 
     *reinterpret_cast<uint4*>(out + ((size_t)blockIdx.z * hp + y) * wp + x) = o;
 }
 
-__global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out) {
+__global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out, int packed) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= ow) return;
     const int b = blockIdx.z;
@@ -211,7 +239,8 @@ __global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_co
     v[6] = (t * a0 + t * a1) * b0 + (t * a0 + t * a1) * b1;  // the timestep plane goes through the same resize arithmetic
 #pragma unroll
     for (int c = 7; c < 16; c++) v[c] = 0.f;
-    store_c8_s2d_16(out, v, oy, ox, oh, ow);
+    if (packed) store_c8_s2d_packed(out, v, oy, ox, oh, ow);
+    else store_c8_s2d_16(out, v, oy, ox, oh, ow);
 }
 
 // Block head for k >= 1 fused with the flow / mask update that follows block k-1
@@ -233,7 +262,7 @@ __global__ void head0_kernel(const __grid_constant__ InBatch ib, const __grid_co
 template <int S, int SP, int MODE, int SPP, bool STORE>
 __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __restrict__ F, float* __restrict__ M, const float* __restrict__ d, int dh, int dw,
                                    const float* __restrict__ dprev, int pdh, int pdw, const float* __restrict__ dpp, int ppdh, int ppdw,
-                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out, int dch) {
+                                   const __grid_constant__ TBatch tb, int hp, int wp, int oh, int ow, __half* __restrict__ out, int dch, int packed) {
     // dch = planes per image of the block outputs d / dprev / dpp: 6 for rife-v4.6 (PixelShuffle of 24 channels, the sixth
     // plane unused), 5 for rife-v4 (the deconvolution's own 5 channels at half the block resolution, so SP = 2 * S_{k-1})
     constexpr bool FIRST = MODE == 0;
@@ -407,7 +436,8 @@ __global__ void head_update_kernel(const __grid_constant__ InBatch ib, float* __
     }
 #pragma unroll
     for (int c = 12; c < 16; c++) v[c] = 0.f;
-    store_c8_s2d_16(out, v, oy, ox, oh, ow);
+    if (packed) store_c8_s2d_packed(out, v, oy, ox, oh, ow);
+    else store_c8_s2d_16(out, v, oy, ox, oh, ow);
 }
 
 // last update + blend + rife_postproc: flownet.param:202-217, src/rife.cpp:4375-4398, mat_pixel.cpp:158

@@ -30,8 +30,6 @@ namespace rife {
 
 namespace {
 
-constexpr int TWP = 64;        // tile width incl. 1-pixel halo left and right -> 62 valid output columns
-constexpr int TVALID = TWP - 2;
 constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,10 +177,21 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) { return (uint32_t
 // input (4 parity sub-images [py][px] of H/2 x W/2, each a run of K chunks): input row 2y+dy-1 is row y-1 of the odd
 // sub-image for dy = 0, row y of the even one for dy = 1 and row y of the odd one for dy = 2 (columns alike), so a
 // chunk of parity (py,px) contributes (py?2:1)*(px?2:1) taps, each again a plain shifted view of the same slab.
-template <int N, int MT, int STAGES, int TAPS>
+// WIDE = 1 (stride-1 convs with 3N <= 256): an accumulator is 128 consecutive pixels of ONE image row instead of 2 rows x 64,
+// the tile is MT rows x 126 columns.  Halo row r is then the dy operand of accumulator r - dy for all three dy, and those
+// accumulators are adjacent in TMEM: ONE MMA of up to 3N columns against [W_dy2 | W_dy1 | W_dy0] updates all of them, so a
+// kernel column costs MT + 2 MMAs instead of 3 MT (2 MT + 1 with the paired issue) and every activation row is fetched from
+// shared memory once instead of three (two) times -- the mainloop of the N <= 64 layers is bound by exactly that fetch
+// (profiles/README.md).  The wrap-around of a shifted 128-pixel view into the next row only reaches output columns 126, 127,
+// which are not stored.
+template <int N, int MT, int STAGES, int TAPS, int WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, TcConvArgs a) {
-    constexpr int ROWS = 2 * MT + 2;              // input rows per tile (halo included)
+    constexpr int TWP = WIDE ? 128 : 64;          // tile width incl. 1-pixel halo left and right
+    constexpr int TVALID = TWP - 2;
+    constexpr int RPA = WIDE ? 1 : 2;             // image rows per accumulator
+    constexpr int ROWS = RPA * MT + 2;            // input rows per tile (halo included)
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;  // bytes of one plane slab: 2 eight-channel halves
+    static_assert(!WIDE || (TAPS == 9 && 3 * N <= 256), "wide tiles: stride-1 convs whose three row taps fit one MMA");
     constexpr int W_BYTES = TAPS * 2 * N * 16;
     constexpr int ACC_COLS = MT * N;              // TMEM columns per accumulator set
     static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         }
         *reinterpret_cast<uint4*>(biasB + (size_t)i * 8) = z;
     }
-    if (a.res_mode == 3 && (a.pair & 2)) {
+    if (a.res_mode == 3 && ((a.pair & 2) || WIDE)) {
         // narrow identity tap: a 16 x 16 identity [half][16 rows][8]; the MMA of K chunk kc targets only the 16 accumulator
         // columns of that chunk's channels (N = 16 instead of N: a quarter of the B bytes, a quarter of the math)
         for (int i = threadIdx.x; i < 2 * 16 * 8; i += NTHREADS) {
@@ -291,13 +300,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
                 const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
-                const int x0 = tx * TVALID, y0 = ty * (2 * MT);
+                const int x0 = tx * TVALID, y0 = ty * (RPA * MT);
                 for (int kc = 0; kc < KC; kc++, it++) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)));
                     for (int p = 0; p < nplanes; p++)
-                        tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * 4, y0 - 1, p * (2 * KC) + 2 * kc, bimg);
+                        tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * (WIDE ? 2 : 4), y0 - 1, p * (2 * KC) + 2 * kc, bimg);  // 16 B per pixel = 4 u32 / 2 u64 elements
                     if (!a.wres) bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                     if (dbg && it - dskip < 12u) dbg[1 + it - dskip] = clock64();
                     if (++s == NST) { s = 0; ph ^= 1; }
@@ -341,8 +350,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_base = (st >> 4) | A_LBO;
                     const uint32_t b_base = ((a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE) >> 4) | B_LBO;
-                    constexpr int ROWSTEP16 = (2 * TWP * 16) >> 4;  // accumulator m+1 starts two tile rows further
-                    if constexpr (TAPS == 9) {
+                    constexpr int ROWSTEP16 = (RPA * TWP * 16) >> 4;  // accumulator m+1 starts RPA tile rows further
+                    if constexpr (WIDE) {
+                        constexpr uint32_t B3_LBO = ((uint32_t)(3 * N * 16) >> 4) << 16;
+                        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                        constexpr uint32_t idesc3 = (1u << 4) | ((uint32_t)((3 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                        const uint32_t b_addr = a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE;
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++) {  // weight block of (kc, dx): [half][3N rows: dy2 | dy1 | dy0][8] (to_wide_layout)
+                            const uint32_t b_lo = ((b_addr + (uint32_t)(dx * (2 * 3 * N * 16))) >> 4) | B3_LBO;
+                            const uint32_t a_lo = a_base + (uint32_t)dx;
+                            if (nplanes == 2) umma_issue_wide<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, idesc2, idesc3, 1u);
+                            else umma_issue_wide<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, idesc2, idesc3, 1u);
+                        }
+                        if (a.res_mode == 3) {  // the self-residual as a narrow identity tap onto the 16 accumulator columns of this K chunk
+                            constexpr uint32_t I16_LBO = ((uint32_t)(16 * 16) >> 4) << 16;
+                            constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                            const uint32_t b_lo = (smem_u32(ident) >> 4) | I16_LBO;
+                            const uint32_t a_lo = a_base + (uint32_t)(((1 * TWP + 1) * 16) >> 4);
+                            const uint32_t accn = acc0 + (uint32_t)(16 * kc);
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
+                        }
+                    } else if constexpr (TAPS == 9) {
                         bool paired = false;
                         if constexpr (2 * N <= 256) paired = (a.pair & 1) != 0;
                         if (paired) {
@@ -427,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate channel blocks
         const int p = q * 32 + lane;  // flattened position inside an accumulator
-        const int xr = p & (TWP - 1), yrow = p >> 6;
+        const int xr = p & (TWP - 1), yrow = WIDE ? 0 : (p >> 6);
         uint32_t tcount = 0;
         const size_t HW = (size_t)a.H * a.W;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
             const uint32_t aph = (tcount >> 1) & 1;
             const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
             const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
-            const int x0 = tx * TVALID, y0 = ty * (2 * MT);
+            const int x0 = tx * TVALID, y0 = ty * (RPA * MT);
             const int x = x0 + xr;
             const __half* res_b = a.res + (size_t)bimg * a.res_bstride;
             __half* out_b = a.out + (size_t)bimg * a.out_bstride;
@@ -451,12 +481,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 const float2 sm1v = make_float2(sm1, sm1);
                 // per-thread output address pieces: block (m, cb) -> obase + m * mstep + cb * cbstep
                 const bool s2d = a.out_s2d != 0;
-                const int yb = y0 + yrow;  // row of accumulator 0; accumulator m is two rows further down each
+                const int yb = y0 + yrow;  // row of accumulator 0; accumulator m is RPA rows further down each
                 const size_t cg_stride = !s2d ? HW : (HW >> 2);
                 const size_t pix0 = !s2d ? (size_t)yb * a.W + x : (size_t)(yb >> 1) * (a.W >> 1) + (x >> 1);
                 const size_t cg_base = !s2d ? 0 : (size_t)((yb & 1) * 2 + (x & 1)) * (a.Cout / 8);
                 __half* const obase = out_b + (cg_base * cg_stride + pix0) * 8;
-                const size_t mstep = (!s2d ? (size_t)2 * a.W : (size_t)(a.W >> 1)) * 8;
+                static_assert(!WIDE || RPA == 1, "");
+                // (space-to-depth output: rows alternate between the two row-parity sub-images, so it needs 2-row accumulators)
+                const size_t mstep = (!s2d ? (size_t)RPA * a.W : (size_t)(a.W >> 1)) * 8;
                 const size_t cbstep = (size_t)(CBL / 8) * cg_stride * 8, gstep = cg_stride * 8;
                 auto ldblk = [&](int blk, uint32_t* r) {
                     const int m = blk / NCBL, cb = blk - m * NCBL;
@@ -471,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 auto stblk = [&](int blk, const uint32_t* r, auto split_tag) {
                     constexpr bool SPLIT = decltype(split_tag)::value;
                     const int m = blk / NCBL, cb = blk - m * NCBL;
-                    if (!(xvalid && yb + 2 * m < a.H)) return;
+                    if (!(xvalid && yb + RPA * m < a.H)) return;
                     __half* op = obase + m * mstep + cb * cbstep;
 #pragma unroll
                     for (int g = 0; g < CBL / 8; g++) {
@@ -523,7 +555,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 const bool has_res = a.res_mode != 0;
                 auto prefetch = [&](int blk, uint4* dst) {
                     const int m = blk / NCB, cb = blk % NCB;
-                    const int y = y0 + 2 * m + yrow;
+                    const int y = y0 + RPA * m + yrow;
                     if (!has_res || !xvalid || y >= a.H) return;
 #pragma unroll
                     for (int g = 0; g < G; g++) {
@@ -534,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 };
                 auto process = [&](int blk, const uint4* rcur) {
                     const int m = blk / NCB, cb = blk % NCB;
-                    const int y = y0 + 2 * m + yrow;
+                    const int y = y0 + RPA * m + yrow;
                     const bool valid = xvalid && y < a.H;
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N + cb * CB;
                     const size_t pix = !a.out_s2d ? (size_t)y * a.W + x : (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
@@ -731,10 +763,11 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int N, int MT, int STAGES, int TAPS>
+template <int N, int MT, int STAGES, int TAPS, int WIDE = 0>
 static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t st) {
     TcConvArgs a = a_in;
-    constexpr int ROWS = 2 * MT + 2;
+    constexpr int TWP = WIDE ? 128 : 64;
+    constexpr int ROWS = (WIDE ? 1 : 2) * MT + 2;
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;
     constexpr int W_BYTES = TAPS * 2 * N * 16;
     const int nplanes = a.split_in ? 2 : 1;
@@ -768,13 +801,13 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     {
         std::lock_guard<std::mutex> lk(configured_mu);
         if (smem > configured[dev]) {
-            if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+            if (cudaFuncSetAttribute(tc_conv3x3_kernel<N, MT, STAGES, TAPS, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
             configured[dev] = smem;
         }
     }
     int ntiles = a.tiles_x * a.tiles_y * a.batch;
     int grid = ntiles < a.num_sms ? ntiles : a.num_sms;
-    tc_conv3x3_kernel<N, MT, STAGES, TAPS><<<grid, NTHREADS, smem, st>>>(tm, a);
+    tc_conv3x3_kernel<N, MT, STAGES, TAPS, WIDE><<<grid, NTHREADS, smem, st>>>(tm, a);
     g_launch_count++;
     return 0;
 }
@@ -783,6 +816,9 @@ int tc_conv_tile_rows(int N) { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }
 
 template <int N, int MT, int STAGES>
 static int launch_n(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+    if constexpr (N == 64) {  // the instance tc_wide_enabled() admits
+        if (a.wide) return launch_t<N, MT, STAGES, 9, 1>(a, tm, st);
+    }
     return a.s2 ? launch_t<N, MT, STAGES, 4>(a, tm, st) : launch_t<N, MT, STAGES, 9>(a, tm, st);
 }
 
@@ -792,8 +828,12 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     if (a.Cin % 16 || a.N % 16 || a.N < 16 || a.N > 256) return -4;
     const int nplanes = a.split_in ? 2 : 1;
     const int MT = tc_conv_tile_rows(a.N) / 2;
+    // wide tiles (one-row accumulators of 128 pixels, MT rows x 126 columns): stride-1 convolutions whose weights were packed
+    // for them (tc_wide_enabled), C8 output in plain (not space-to-depth) form
+    a.wide = (!a.s2 && a.epi == TC_EPI_C8 && !a.out_s2d && tc_wide_enabled(a.N)) ? 1 : 0;
+    const int TWP = a.wide ? 128 : 64, TVALID = TWP - 2, tile_rows = a.wide ? MT : 2 * MT;
     a.tiles_x = (a.W + TVALID - 1) / TVALID;
-    a.tiles_y = (a.H + 2 * MT - 1) / (2 * MT);
+    a.tiles_y = (a.H + tile_rows - 1) / tile_rows;
     if (!a.num_sms) a.num_sms = 148;
     // activation tensor viewed as [planes * C/8][H][W*4] 32-bit words (16 B = one pixel's 8 channels)
     CUtensorMap tm;
@@ -807,15 +847,18 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     if (ident_ok && a.res_mode == 1 && a.epi == TC_EPI_C8 && !a.s2 && a.res == (const __half*)in && a.Cin == a.N && a.Cout == a.N && a.N <= 128 && (!a.res_split) == (!a.split_in) &&
         (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
         a.res_mode = 3;
-    a.pair = (!a.s2 && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
+    a.pair = (!a.s2 && !a.wide && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
     if (tc_pair_mode() & 2) a.pair |= 2;  // narrow identity tap for the self-residual layers (independent of the weight layout)
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
-    cuuint64_t dims[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
+    // one pixel's 8 channels = 16 bytes = 4 u32 elements (64-pixel boxes) or 2 u64 elements (128-pixel boxes: a box dimension
+    // holds at most 256 elements)
+    const int epp = a.wide ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)a.W * epp, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
     cuuint64_t strides[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16, a.batch > 1 ? (cuuint64_t)a.in_bstride * 2 : (cuuint64_t)img_bytes};
-    cuuint32_t box[4] = {(cuuint32_t)TWP * 4, (cuuint32_t)(2 * MT + 2), 2, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(TWP * epp), (cuuint32_t)(tile_rows + 2), 2, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&tm, a.wide ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -5;
     switch (a.N) {
@@ -899,6 +942,27 @@ int tc_pair_mode() {
     return mode;
 }
 bool tc_pair_enabled(int N) { return (tc_pair_mode() & 1) && 2 * N <= 256; }
+// Wide tiles (kernel template WIDE; RIFE_B200_WIDE, default TC_WIDE_DEFAULT): stride-1 convolutions with N = 64 -- the residual
+// chain of IFBlock 3, 44 % of the model's FLOPs.  (3N <= 256 would also admit N = 32 / 48; those layers run on maps too narrow
+// for 126-column tiles to pay.)  Packers and launcher consult the same function.
+bool tc_wide_enabled(int N) {
+    static const int on = getenv("RIFE_B200_WIDE") ? atoi(getenv("RIFE_B200_WIDE")) : TC_WIDE_DEFAULT;
+    return on && N == 64;
+}
+// [kc][tap = dy*3+dx][half][N][8] -> [kc][dx][half][3N rows: dy2 | dy1 | dy0][8]
+static void to_wide_layout(std::vector<uint16_t>& w, int kcs, int N) {
+    std::vector<uint16_t> o(w.size());
+    for (int kc = 0; kc < kcs; kc++)
+        for (int dy = 0; dy < 3; dy++)
+            for (int dx = 0; dx < 3; dx++)
+                for (int hf = 0; hf < 2; hf++)
+                    for (int n = 0; n < N; n++) {
+                        const size_t src = ((((size_t)kc * 9 + dy * 3 + dx) * 2 + hf) * N + n) * 8;
+                        const size_t dst = ((((size_t)kc * 3 + dx) * 2 + hf) * (3 * N) + (size_t)(2 - dy) * N + n) * 8;
+                        for (int j = 0; j < 8; j++) o[dst + j] = w[src + j];
+                    }
+    w.swap(o);
+}
 // [kc][tap = dy*3+dx][half][N][8] -> [kc][dx][half][3N rows: dy2 | dy0 | dy1][8]
 static void to_paired_layout(std::vector<uint16_t>& w, int kcs, int N) {
     std::vector<uint16_t> o(w.size());
@@ -926,7 +990,9 @@ void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<
                         __half h = __float2half_rn(w[((size_t)n * cin + ic) * 9 + tap]);
                         out[((((size_t)kc * 9 + tap) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
                     }
-    if (paired < 0 ? tc_pair_enabled(N) : (paired != 0 && 2 * N <= 256)) to_paired_layout(out, cin / 16, N);
+    // paired: -1 = what the launcher will assume for a stride-1 conv of this N; 0 plain; 1 paired; 2 wide
+    if (paired == 2 || (paired < 0 && tc_wide_enabled(N))) { if (3 * N <= 256) to_wide_layout(out, cin / 16, N); }
+    else if (paired < 0 ? tc_pair_enabled(N) : (paired != 0 && 2 * N <= 256)) to_paired_layout(out, cin / 16, N);
 }
 // conv 3x3 stride 2: w[oc][ic][3][3] -> wpk[4 parities][cinp/16][4 slots][2][N][8]; parity (py,px) of the space-to-depth
 // input, slot (iy*2+ix) <-> tap dy = py ? 2*iy : 1, dx = px ? 2*ix : 1; input channels zero padded to cinp

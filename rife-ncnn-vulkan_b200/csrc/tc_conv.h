@@ -34,6 +34,7 @@ struct TcConvArgs {
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
+    int wide;                       // filled by the launcher: one-row accumulators / 126-column tiles (tc_wide_enabled)
     int pair;                       // filled by the launcher: bit 0 paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled), bit 1 narrow identity tap
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
     int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
@@ -48,11 +49,13 @@ int tc_conv_tile_rows(int N);
 constexpr int TC_PAIR_DEFAULT = 3;
 int tc_pair_mode();
 bool tc_pair_enabled(int N);
+constexpr int TC_WIDE_DEFAULT = 1;
+bool tc_wide_enabled(int N);
 
 void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
 void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
 
-// paired: -1 = as tc_pair_enabled(N) says (what the launcher will assume), 0 / 1 = explicit (diagnostics)
+// paired: -1 = what the launcher will assume for this N (tc_wide_enabled / tc_pair_enabled), 0 plain / 1 paired / 2 wide = explicit (diagnostics)
 void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out, int paired = -1);
 void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, std::vector<uint16_t>& out);
 void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out, int paired = -1);

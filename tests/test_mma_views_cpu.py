@@ -120,3 +120,49 @@ def test_deconv_views_paired_equals_unpaired(pkg):
                         continue
                     s += float(np.dot(x[:, ty // 2, tx // 2], w[oc, :, ky, kx]))
             assert abs(a1[m, p, par * ocs + oc] - s) < 1e-3, (par, oc, a1[m, p, par * ocs + oc], s)
+
+
+# ---- wide tiles (kernel template WIDE): one-row accumulators of 128 pixels, [dy2 | dy1 | dy0] weight blocks ------------------
+WTW = 128
+
+
+def _a_view_wide(slab, rows, start16):
+    """A operand (128 x 16) from a wide slab [2 halves][rows][128 px][8]: 128 consecutive pixels from start16 (wraps into the
+    next row for dx > 0; behind the last row: the overrun pad)."""
+    flat = slab.reshape(2, rows * WTW, 8)
+    flat = np.concatenate([flat, np.zeros((2, 64, 8), np.float32)], axis=1)
+    return np.concatenate([flat[0, start16:start16 + 128], flat[1, start16:start16 + 128]], axis=1)
+
+
+def _accumulate_wide(slabs, wpk, N, MT):
+    """umma_issue_wide (tools/gen_mma_issue.py wide_block): per kernel column dx, halo row r feeds accumulators r - dy."""
+    rows = MT + 2
+    kcs = len(slabs)
+    acc = np.zeros((128, MT * N), np.float64)
+    wk = wpk.reshape(kcs, -1)
+    for kc in range(kcs):
+        for dx in range(3):
+            blk = dx * 2 * 3 * N
+            for r in range(MT + 2):
+                dy_max, dy_min = min(2, r), max(0, r - (MT - 1))
+                ncol = (dy_max - dy_min + 1) * N
+                A = _a_view_wide(slabs[kc], rows, dx + r * WTW)
+                B = _b_view(wk[kc], blk + (2 - dy_max) * N, 3 * N, ncol)
+                c0 = (r - dy_max) * N
+                acc[:, c0:c0 + ncol] += A @ B.T
+    return acc.reshape(128, MT, N).transpose(1, 0, 2)
+
+
+@pytest.mark.parametrize("cin,cout,N,MT", [(64, 64, 64, 4), (32, 64, 64, 4)])
+def test_conv3x3_wide_views_equal_direct(pkg, cin, cout, N, MT):
+    rng = np.random.default_rng(cin + 3 * N)
+    w = (rng.standard_normal((cout, cin, 3, 3)) * 0.1).astype(np.float16).astype(np.float32)
+    rows = MT + 2
+    x = rng.standard_normal((cin, rows, WTW)).astype(np.float16).astype(np.float32)
+    slabs = [x[kc * 16:(kc + 1) * 16].reshape(2, 8, rows, WTW).transpose(0, 2, 3, 1).copy() for kc in range(cin // 16)]
+    acc = _accumulate_wide(slabs, _pack(pkg, 0, w, cout, cin, N, 0, 2), N, MT)
+    for m in range(MT):  # position p of accumulator m: output row m, column p (valid < 126)
+        for p in range(0, WTW - 2, 7):
+            patch = x[:, m:m + 3, p:p + 3]
+            want = np.tensordot(w, patch, axes=([1, 2, 3], [0, 1, 2]))
+            assert np.allclose(acc[m, p, :cout], want, atol=1e-3), (m, p)

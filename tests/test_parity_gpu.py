@@ -492,3 +492,31 @@ def test_null_frame_in_a_batch_is_rejected_before_anything_is_queued(pkg):
     ok = r.process(frames[0], frames[1], 0.5)
     r.close()
     assert ok.std() > 5
+
+
+@pytest.mark.parametrize("model", ["rife-v4.6", "rife-v4"])
+@pytest.mark.parametrize("case", ["synth", "large_motion", "readme_images"])
+def test_packed_head_tensors_stay_within_one_lsb(pkg, model, case):
+    """Option "head_pack": the block-head tensors as ONE fp16 plane whose slots 12..15 carry the lo parts of the four flow
+    channels (fused_v46_kernels.cuh: 32 instead of 64 bytes per pixel, half the tensor work in the first stride-2 conv).
+    Same +-1 LSB / 50 dB bar against the oracle as the default."""
+    _need(model)
+    if case == "synth":
+        a, b = parity.synth.pair(640, 360)
+    elif case == "large_motion":
+        a, b = parity.synth.pair(640, 352, dx=24, dy=16)
+    else:
+        try:
+            from PIL import Image
+            d = os.path.join(parity.REF_DIR, "images")
+            a = np.array(Image.open(os.path.join(d, "0.png")).convert("RGB"))
+            b = np.array(Image.open(os.path.join(d, "1.png")).convert("RGB"))
+        except Exception:
+            pytest.skip("README frames or PIL not available")
+    opts = {"head_pack": 1}
+    if a.shape[1] % 32:
+        opts["cpu_crop_quirk"] = 1
+    ref, _ = parity.run_oracle(model, a, b, 0.5)
+    out = parity.run_gpu(pkg, model, a, b, 0.5, options=opts)
+    res = parity.compare(out, ref)
+    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["share_ne"] < 0.02, res

@@ -91,3 +91,18 @@ def test_conv3x3_stride2(pkg, cin, cout):
     o_tc, o_ref = pkg.selftest_conv(2, x, wgt, b, slope=0.2, split=True)
     mx, tol, bad = _check(o_tc, o_ref, 1)
     assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
+@pytest.mark.parametrize("split", [1, 0])
+@pytest.mark.parametrize("self_res", [True, False])
+@pytest.mark.parametrize("h,w", [(11, 140), (4, 126), (5, 127), (9, 300)])
+def test_conv3x3_wide_tiles(pkg, h, w, self_res, split):
+    """N = 64 runs on the wide-tile variant (one-row accumulators of 128 pixels, 126 valid columns, rows in groups of 4; one
+    MMA of up to 192 columns feeds three accumulators): several column tiles, ragged last column and row tiles, the
+    self-residual identity tap and the epilogue residual."""
+    c = 64
+    x, wgt, b, res = _data(c, c, h, w, 9, seed=h * 1000 + w)
+    x = np.ascontiguousarray(x, np.float32)
+    o_tc, o_ref = pkg.selftest_conv(0, x, wgt, b, res=x if self_res else res, slope=0.2, split=bool(split))
+    mx, tol, bad = _check(o_tc, o_ref, split)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))

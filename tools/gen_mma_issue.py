@@ -61,6 +61,32 @@ def pair_block(mt, np_):
             % (body, ", ".join(ops)))
 
 
+def wide_block(mt, np_):
+    """One-row accumulators (128 consecutive pixels of ONE image row each): halo row r is the dy operand of accumulator r - dy
+    for dy = 0, 1, 2, i.e. of up to THREE accumulators that are adjacent in TMEM, so ONE MMA of up to 3N columns against
+    [W_dy2 | W_dy1 | W_dy0] updates all of them: mt + 2 MMAs per kernel column instead of 3 * mt, the activation row is read
+    from shared memory once instead of three times."""
+    lines = ['"{\\n"', '".reg .pred q, p, pt;\\n"', '".reg .b64 da, db;\\n"', '".reg .b32 al, tm, bl;\\n"', '"elect.sync _|q, 0xffffffff;\\n"',
+             '"setp.ne.b32 p, %7, 0;\\n"', '"setp.eq.b32 pt, 0, 0;\\n"']
+    ops = []
+    k = 0
+    for r in range(mt + 2):
+        dy_max, dy_min = min(2, r), max(0, r - (mt - 1))
+        ncol = dy_max - dy_min + 1            # accumulators covered
+        idc = {1: "%4", 2: "%5", 3: "%6"}[ncol]
+        for pl in range(np_):
+            ia, it, ib = 8 + 3 * k, 9 + 3 * k, 10 + 3 * k
+            lines += ['"add.u32 al, %%1, %%%d;\\n"' % ia, '"add.u32 tm, %%0, %%%d;\\n"' % it, '"add.u32 bl, %%2, %%%d;\\n"' % ib, '"mov.b64 da, {al, %3};\\n"', '"mov.b64 db, {bl, %3};\\n"']
+            pred = "p" if pl == 0 else "pt"
+            lines.append('"@q tcgen05.mma.cta_group::1.kind::f16 [tm], da, db, %s, %s;\\n"' % (idc, pred))
+            ops += ['"n"(%d * APLANE16 + %d * ROWSTEP16)' % (pl, r), '"n"(%d * NCOLS)' % (r - dy_max), '"n"(%d * NCOLS)' % (2 - dy_max)]
+            k += 1
+    lines.append('"}\\n"')
+    body = "\n            ".join(lines)
+    return ("        asm volatile(\n            %s\n            ::\"r\"(acc), \"r\"(a_lo), \"r\"(b_lo), \"r\"(desc_hi), \"r\"(idesc), \"r\"(idesc2), \"r\"(idesc3), \"r\"(accumulate), %s);\n"
+            % (body, ", ".join(ops)))
+
+
 def main():
     o = ["// Generated by tools/gen_mma_issue.py -- do not edit.  One asm block per filter tap issues all MT x NP MMAs of that tap;",
          "// descriptor / TMEM address arithmetic stays inside the block so ptxas keeps it on the uniform datapath.",
@@ -86,6 +112,18 @@ def main():
         for np_ in (1, 2):
             o.append("    %sif constexpr (MT == %d && NP == %d) {" % ("" if first else "else ", mt, np_))
             o.append(pair_block(mt, np_).rstrip("\n"))
+            o.append("    }")
+            first = False
+    o.append("}")
+    o += ["// Wide issue (see tools/gen_mma_issue.py wide_block): one-row accumulators, the halo rows of one kernel column.  b_lo addresses",
+          "// the [dy2 | dy1 | dy0] weight block of that column (rows of 16 B); idesc / idesc2 / idesc3 = N / 2N / 3N columns.",
+          "template <int MT, int NP, int APLANE16, int ROWSTEP16, int NCOLS>",
+          "__device__ __forceinline__ void umma_issue_wide(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t idesc2, uint32_t idesc3, uint32_t accumulate) {"]
+    first = True
+    for mt in (2, 4):
+        for np_ in (1, 2):
+            o.append("    %sif constexpr (MT == %d && NP == %d) {" % ("" if first else "else ", mt, np_))
+            o.append(wide_block(mt, np_).rstrip("\n"))
             o.append("    }")
             first = False
     o.append("}")
