@@ -444,6 +444,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--plain-blocks", type=int, default=-1, help="bit mask of IFBlocks whose residual chain uses plain fp16 activations (-1 = library default)")
     ap.add_argument("--recompute-fm", type=int, default=-1, help="fused path: rebuild the full-resolution flow / mask planes instead of storing them (0, 1, 2; -1 = library default)")
+    ap.add_argument("--head-pack", type=int, default=-1, help="fused path: packed block-head tensors (0 / 1; -1 = library default)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per lock-step batch on the fused path (0 = auto from the frame size)")
     ap.add_argument("--model", default=MODEL, help="model directory name (default rife-v4.6 = the BASELINE metric; others are side measurements)")
     ap.add_argument("--tta", action="store_true")
@@ -460,7 +461,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa(local) if world > 1 else "not bound (single process)"
+    numa = bind_to_gpu_numa(local)  # pinned host buffers next to the GPU: the e2e legs are bound by the host link
 
     import torch
     import __graft_entry__ as g
@@ -499,6 +500,8 @@ def main():
         eng.set_option("plain_blocks", args.plain_blocks)
     if args.recompute_fm >= 0:
         eng.set_option("recompute_fm", args.recompute_fm)
+    if args.head_pack >= 0:
+        eng.set_option("head_pack", args.head_pack)
 
     ctx = Ctx()
     ctx.pkg, ctx.eng, ctx.dist, ctx.world, ctx.rank, ctx.local = pkg, eng, dist, world, rank, local
@@ -548,7 +551,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
                            "tta_temporal": args.tta_temporal, "pairs_per_step": head["pairs_per_step_all_ranks"], "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch,
-                           "images_per_lockstep_batch": head["kb"], "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "recompute_fm": eng.get_option("recompute_fm"),
+                           "images_per_lockstep_batch": head["kb"], "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "recompute_fm": eng.get_option("recompute_fm"), "head_pack": eng.get_option("head_pack"),
+                           "wide_tiles": int(os.environ.get("RIFE_B200_WIDE", "1")),
                            "fused_path": head["fast"], "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic",
                            "host_numa": numa},
                 "gflop_per_frame": hb["gflop_per_frame"], "model_tflops": hb["value"] * GFLOP_PER_FRAME[args.workload] / 1000.0 if plain_v46 else None,

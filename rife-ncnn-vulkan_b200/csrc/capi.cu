@@ -491,7 +491,7 @@ extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int ci
 extern "C" int rife_b200_debug_hbm(int gpuid, void* cuda_stream, int which, int w, int h, int c, int iters, const void* in, const void* in2, void* out) {
     GUARD_BEGIN
     using namespace rife;
-    if (w <= 0 || h <= 0 || c <= 0 || which < 0 || which > 5 || iters < 0) return RIFE_B200_ERR_ARG;
+    if (w <= 0 || h <= 0 || c < (which == 4 ? 0 : 1) || which < 0 || which > 5 || iters < 0) return RIFE_B200_ERR_ARG;
     if (iters == 0 && (!in || !out)) return RIFE_B200_ERR_ARG;
     if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
     cudaStream_t st = (cudaStream_t)cuda_stream;

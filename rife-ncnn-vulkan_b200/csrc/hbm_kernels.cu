@@ -40,7 +40,11 @@ __device__ __forceinline__ size_t orient_index(int o, int y, int x, int wp, int 
 // preproc: u8 HWC -> float planes * (1/255), zero outside (w, h); all `norient` orientations from ONE read of the frame.
 // out: orientation o at out + o * 3 * wp * hp.  Per pixel: 3 B read, norient * 12 B written.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) preproc_kernel(const uint8_t* __restrict__ rgb, int w, int h, float* __restrict__ out, int wp, int hp, int norient, int bgr) {
+// thread t of the 256 owns, per channel and orientation, ONE float4: four consecutive pixels along the fastest axis of that
+// orientation's plane (x for the row-major views, y for the transposed ones; reversed views write the four values in reverse
+// order) -- 512-byte warp stores, 3 per orientation.
+__device__ __forceinline__ float4 rev4(float4 v, bool r) { return r ? make_float4(v.w, v.z, v.y, v.x) : v; }
+__global__ void __launch_bounds__(256, 4) preproc_kernel(const uint8_t* __restrict__ rgb, int w, int h, float* __restrict__ out, int wp, int hp, int norient, int bgr) {
     __shared__ float tile[3][TS][TS + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
@@ -60,16 +64,24 @@ __global__ void __launch_bounds__(256) preproc_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     const size_t plane = (size_t)wp * hp;
+    const int a = threadIdx.x >> 3, b4 = (threadIdx.x & 7) * 4;  // slow index, first of the four fast indices
+#pragma unroll 1
     for (int o = 0; o < norient; o++) {
         float* dst = out + (size_t)o * 3 * plane;
+        // flips of this orientation along its fast / slow plane axis (Appendix B): o = 1, 2: x reversed; 2, 3: y reversed;
+        // transposed views: 5, 6: y (fast) reversed; 6, 7: x (slow) reversed
+        const bool tr = o >= 4;
+        const bool rf = tr ? (o == 5 || o == 6) : (o == 1 || o == 2);
+        const bool rs = tr ? (o == 6 || o == 7) : (o == 2 || o == 3);
+        const int nf = tr ? hp : wp, ns = tr ? wp : hp;          // extents of the fast / slow plane axes
+        const int f0 = (tr ? y0 : x0) + b4, s0 = (tr ? x0 : y0) + a;
+        const size_t di = (size_t)(rs ? ns - 1 - s0 : s0) * nf + (rf ? nf - 4 - f0 : f0);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int a = ty + 8 * k;
-            // row-major views: lane = x.  transposed views: lane = y (the fastest index of the [wp][hp] plane)
-            const int yl = o < 4 ? a : tx, xl = o < 4 ? tx : a;
-            const size_t di = orient_index(o, y0 + yl, x0 + xl, wp, hp);
-#pragma unroll
-            for (int c = 0; c < 3; c++) dst[c * plane + di] = tile[c][yl][xl];
+        for (int c = 0; c < 3; c++) {
+            float4 v;
+            if (!tr) v = make_float4(tile[c][a][b4], tile[c][a][b4 + 1], tile[c][a][b4 + 2], tile[c][a][b4 + 3]);
+            else v = make_float4(tile[c][b4][a], tile[c][b4 + 1][a], tile[c][b4 + 2][a], tile[c][b4 + 3][a]);
+            *reinterpret_cast<float4*>(dst + c * plane + di) = rev4(v, rf);
         }
     }
 }
@@ -92,7 +104,7 @@ __device__ __forceinline__ uint8_t quant(float v) {
 }
 // no spatial TTA: four pixels per thread; 16-byte plane reads and 12-byte (3 x u32) frame writes when the row geometry allows
 template <int N_IN>
-__global__ void __launch_bounds__(256) postproc_plain_kernel(PostArgs pa, int wp, int hp, uint8_t* __restrict__ rgb, int w, int h, int cpu_contig, int bgr, int vec) {
+__global__ void __launch_bounds__(128) postproc_plain_kernel(PostArgs pa, int wp, int hp, uint8_t* __restrict__ rgb, int w, int h, int cpu_contig, int bgr, int vec) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x >= w) return;
     const size_t plane = (size_t)wp * hp;
@@ -131,48 +143,61 @@ __global__ void __launch_bounds__(256) postproc_plain_kernel(PostArgs pa, int wp
         for (int j = 0; j < 4 && x + j < w; j++) { dst[j * 3] = o[j * 3]; dst[j * 3 + 1] = o[j * 3 + 1]; dst[j * 3 + 2] = o[j * 3 + 2]; }
     }
 }
-// spatial TTA: input i is orientation i & 7 of the padded frame (set i >> 3: forward / time-reversed)
+// spatial TTA: input i is orientation i & 7 of the padded frame (set i >> 3: forward / time-reversed).  Same float4-per-thread
+// scheme as preproc_kernel: row-major inputs are read in place, transposed ones through a padded shared-memory tile.
 template <int NSET>
-__global__ void __launch_bounds__(256) postproc_tta_kernel(PostArgs pa, int wp, int hp, uint8_t* __restrict__ rgb, int w, int h, int bgr) {
+__global__ void __launch_bounds__(256, 3) postproc_tta_kernel(PostArgs pa, int wp, int hp, uint8_t* __restrict__ rgb, int w, int h, int bgr, int vec) {
     __shared__ float T[4][TS][TS + 1];  // the transposed orientations 4-7 of one channel: T[o - 4][x][y]
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
     const size_t plane = (size_t)wp * hp;
+    const int a = threadIdx.x >> 3, b4 = (threadIdx.x & 7) * 4;
     float acc[3][4];
+#pragma unroll 1
     for (int q = 0; q < 3; q++) {
         float mean[NSET][4];
 #pragma unroll
         for (int s = 0; s < NSET; s++) {
             __syncthreads();
 #pragma unroll
+            for (int o = 4; o < 8; o++) {  // x = x0 + a (slow axis of the [wp][hp] plane), y = y0 + b4 .. + 3 (fast)
+                const bool rf = o == 5 || o == 6, rs = o == 6 || o == 7;
+                const size_t si = (size_t)(rs ? wp - 1 - (x0 + a) : x0 + a) * hp + (rf ? hp - 4 - (y0 + b4) : y0 + b4);
+                const float4 v = rev4(*reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si), rf);
+                T[o - 4][a][b4] = v.x; T[o - 4][a][b4 + 1] = v.y; T[o - 4][a][b4 + 2] = v.z; T[o - 4][a][b4 + 3] = v.w;
+            }
+            __syncthreads();
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};  // rife.cpp:4060-4144: the eight values are added in orientation order, then / 8
+#pragma unroll
+            for (int o = 0; o < 4; o++) {  // y = y0 + a, x = x0 + b4 .. + 3
+                const bool rf = o == 1 || o == 2, rs = o == 2 || o == 3;
+                const size_t si = (size_t)(rs ? hp - 1 - (y0 + a) : y0 + a) * wp + (rf ? wp - 4 - (x0 + b4) : x0 + b4);
+                const float4 v = rev4(*reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si), rf);
+                sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+            }
+#pragma unroll
             for (int o = 4; o < 8; o++)
 #pragma unroll
-                for (int k = 0; k < 4; k++) {  // lane = y: contiguous in the [wp][hp] plane
-                    const int xl = ty + 8 * k;
-                    T[o - 4][xl][tx] = pa.in[s * 8 + o][q * plane + orient_index(o, y0 + tx, x0 + xl, wp, hp)];
-                }
-            __syncthreads();
+                for (int j = 0; j < 4; j++) sum[j] += T[o - 4][b4 + j][a];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int yl = ty + 8 * k;
-                float sum = 0.f;  // rife.cpp:4060-4144: the eight values are added in orientation order, then / 8
-#pragma unroll
-                for (int o = 0; o < 4; o++) sum += pa.in[s * 8 + o][q * plane + orient_index(o, y0 + yl, x0 + tx, wp, hp)];
-#pragma unroll
-                for (int o = 4; o < 8; o++) sum += T[o - 4][tx][yl];
-                mean[s][k] = sum / 8;
-            }
+            for (int j = 0; j < 4; j++) mean[s][j] = sum[j] / 8;
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) acc[q][k] = NSET == 2 ? (mean[0][k] + mean[NSET - 1][k]) * 0.5f * 255.f + 0.5f : mean[0][k] * 255.f + 0.5f;
+        for (int j = 0; j < 4; j++) acc[q][j] = NSET == 2 ? (mean[0][j] + mean[NSET - 1][j]) * 0.5f * 255.f + 0.5f : mean[0][j] * 255.f + 0.5f;
     }
+    const int x = x0 + b4, y = y0 + a;
+    if (x >= w || y >= h) return;
+    uint8_t o8[12];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = x0 + tx, y = y0 + ty + 8 * k;
-        if (x >= w || y >= h) continue;
-        uint8_t* dst = rgb + ((size_t)y * w + x) * 3;
+    for (int j = 0; j < 4; j++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) dst[bgr ? 2 - q : q] = quant(acc[q][k]);
+        for (int q = 0; q < 3; q++) o8[j * 3 + (bgr ? 2 - q : q)] = quant(acc[q][j]);
+    uint8_t* dst = rgb + ((size_t)y * w + x) * 3;
+    if (vec) {  // w % 4 == 0 and a 4-byte aligned frame: the thread's 12 bytes are three aligned words
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+        for (int k = 0; k < 3; k++) d32[k] = (uint32_t)o8[4 * k] | ((uint32_t)o8[4 * k + 1] << 8) | ((uint32_t)o8[4 * k + 2] << 16) | ((uint32_t)o8[4 * k + 3] << 24);
+    } else {
+        for (int j = 0; j < 4 && x + j < w; j++) { dst[j * 3] = o8[j * 3]; dst[j * 3 + 1] = o8[j * 3 + 1]; dst[j * 3 + 2] = o8[j * 3 + 2]; }
     }
 }
 void launch_postproc(const float* const* ins, int n_in, int wp, int hp, uint8_t* rgb, int w, int h, int cpu_contig, int bgr, cudaStream_t st) {
@@ -182,13 +207,14 @@ void launch_postproc(const float* const* ins, int n_in, int wp, int hp, uint8_t*
         // 16-byte reads need idx % 4 == 0 for every row; u32 writes need (y*w + x) * 3 % 4 == 0: both hold iff w % 4 == 0
         // (wp is a multiple of 32) and the frame pointer is 4-byte aligned
         const int vec = (w % 4 == 0) && (((uintptr_t)rgb & 3) == 0);
-        dim3 g(cdiv((size_t)(w + 3) / 4, 64), h);
-        if (n_in == 1) postproc_plain_kernel<1><<<g, 64, 0, st>>>(pa, wp, hp, rgb, w, h, cpu_contig && w != wp, bgr, vec);
-        else postproc_plain_kernel<2><<<g, 64, 0, st>>>(pa, wp, hp, rgb, w, h, cpu_contig && w != wp, bgr, vec);
+        dim3 g(cdiv((size_t)(w + 3) / 4, 128), h);
+        if (n_in == 1) postproc_plain_kernel<1><<<g, 128, 0, st>>>(pa, wp, hp, rgb, w, h, cpu_contig && w != wp, bgr, vec);
+        else postproc_plain_kernel<2><<<g, 128, 0, st>>>(pa, wp, hp, rgb, w, h, cpu_contig && w != wp, bgr, vec);
     } else {
+        const int vec = (w % 4 == 0) && (((uintptr_t)rgb & 3) == 0);
         dim3 g(wp / TS, hp / TS);
-        if (n_in == 8) postproc_tta_kernel<1><<<g, 256, 0, st>>>(pa, wp, hp, rgb, w, h, bgr);
-        else postproc_tta_kernel<2><<<g, 256, 0, st>>>(pa, wp, hp, rgb, w, h, bgr);
+        if (n_in == 8) postproc_tta_kernel<1><<<g, 256, 0, st>>>(pa, wp, hp, rgb, w, h, bgr, vec);
+        else postproc_tta_kernel<2><<<g, 256, 0, st>>>(pa, wp, hp, rgb, w, h, bgr, vec);
     }
     g_launch_count++;
 }
@@ -264,13 +290,14 @@ void launch_temporal_merge_v2(float* f, float* fr, size_t n, int has_mask, cudaS
 struct Flow8 {
     float* f[8];
 };
-__global__ void __launch_bounds__(256) flow_tta_avg_kernel(Flow8 F, int nch, int fw, int fh) {
+__global__ void __launch_bounds__(256, 3) flow_tta_avg_kernel(Flow8 F, int nch, int fw, int fh) {
     __shared__ float T[4][2][TS][TS + 1];  // transposed orientations 4-7, two channels: T[o - 4][c][x][y]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
     const size_t plane = (size_t)fw * fh;
     const int npair = nch >= 4 ? 2 : 1;
     const int ngroups = npair + (nch == 5 ? 1 : 0);
+#pragma unroll 1
     for (int g = 0; g < ngroups; g++) {
         const bool mask = g == npair;
         const size_t cx = (size_t)(mask ? 4 : 2 * g) * plane, cy = (size_t)(mask ? 4 : 2 * g + 1) * plane;
@@ -348,7 +375,7 @@ template <int CG>
 __global__ void __launch_bounds__(128) warp_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out, int c, int h, int w) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    const size_t hw = (size_t)h * w, pi = (size_t)y * w + x;
+    const int hw = h * w, pi = y * w + x;  // one plane holds fewer than 2^31 elements (frames up to 32k x 32k / 4)
     const float sx = x + __ldg(flow + pi), sy = y + __ldg(flow + hw + pi);
     int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
     int x1 = x0 + 1, y1 = y0 + 1;
@@ -357,13 +384,15 @@ __global__ void __launch_bounds__(128) warp_kernel(const float* __restrict__ img
     x1 = min(max(x1, 0), w - 1);
     y1 = min(max(y1, 0), h - 1);
     const float alpha = sx - x0, beta = sy - y0;
-    const size_t i00 = (size_t)y0 * w + x0, i01 = (size_t)y0 * w + x1, i10 = (size_t)y1 * w + x0, i11 = (size_t)y1 * w + x1;
+    const int i00 = y0 * w + x0, i01 = y0 * w + x1, i10 = y1 * w + x0, i11 = y1 * w + x1;
     const int q0 = blockIdx.z * CG;
+    img += (size_t)q0 * hw;
+    out += (size_t)q0 * hw;
     float v0[CG], v1[CG], v2[CG], v3[CG];
 #pragma unroll
     for (int j = 0; j < CG; j++) {
         if (q0 + j < c) {
-            const float* p = img + (size_t)(q0 + j) * hw;
+            const float* p = img + j * hw;
             v0[j] = __ldg(p + i00); v1[j] = __ldg(p + i01); v2[j] = __ldg(p + i10); v3[j] = __ldg(p + i11);
         }
     }
@@ -372,7 +401,7 @@ __global__ void __launch_bounds__(128) warp_kernel(const float* __restrict__ img
         if (q0 + j < c) {
             const float v4 = v0[j] * (1 - alpha) + v1[j] * alpha;
             const float v5 = v2[j] * (1 - alpha) + v3[j] * alpha;
-            out[(size_t)(q0 + j) * hw + pi] = v4 * (1 - beta) + v5 * beta;
+            out[j * hw + pi] = v4 * (1 - beta) + v5 * beta;
         }
     }
 }
