@@ -128,6 +128,7 @@ int rife_b200_debug_conv_timeline(int gpuid, int cin, int cout, int h, int w, in
  * mode 1: deconv4x4 s2 p1 (+bias) followed by PixelShuffle(ps), in [cin][h][w] -> out [cout/(ps*ps)][2h*ps][2w*ps]
  * mode 3: mode 1 with cout = 24, ps = 2, storing only the first five output planes (the IFNet flow head; plane 5 of
  *         out_tc is left untouched)
+ * mode 4: conv5x5 s1 p2 (+bias, + optional residual, + leaky), weight [cout][cin][5][5] (the 5x5 row-stage variant of the kernel)
  * split != 0 stores activations as split-fp16 (hi+lo) for the tensor-core path. */
 int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, int h, int w, int split, int ps, const float* in,
                             const float* weight, const float* bias, const float* res, float slope, float* out_tc,

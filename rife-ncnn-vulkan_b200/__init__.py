@@ -235,7 +235,7 @@ def selftest_conv(mode, x, weight, bias, res=None, slope=0.2, split=True, ps=2, 
     cout = weight.shape[0]
     if mode == 3:
         assert ps == 2 and cout == 24
-    if mode == 0:
+    if mode in (0, 4):
         oshape = (cout, h, w)
     elif mode == 2:
         oshape = (cout, h // 2, w // 2)

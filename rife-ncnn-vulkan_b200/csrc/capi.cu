@@ -258,27 +258,28 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     if (cudaSetDevice(gpuid) != cudaSuccess) return RIFE_B200_ERR_DEVICE;
     cudaStream_t st = 0;
     const size_t hw = (size_t)h * w;
-    const int kk = mode == 0 ? 9 : 16;
+    const int kk = mode == 0 ? 9 : (mode == 4 ? 25 : 16);
     // fp16-exact weights, as in the model files
     std::vector<float> wq((size_t)cout * cin * kk);
     for (size_t i = 0; i < wq.size(); i++) wq[i] = __half2float(__float2half_rn(weight[i]));
     int N, ocs = 0;
     std::vector<uint16_t> wpk;
-    if (mode == 0) {
+    if (mode == 0 || mode == 4) {
         N = (cout + 15) / 16 * 16;
         if (N != cout) return RIFE_B200_ERR_ARG;
-        pack_conv3x3_weights(wq.data(), cout, cin, N, wpk);
+        if (mode == 0) pack_conv3x3_weights(wq.data(), cout, cin, N, wpk);
+        else pack_conv5x5_weights(wq.data(), cout, cin, N, wpk);
     } else {
         ocs = (cout + 7) / 8 * 8;
         N = 4 * ocs;
         pack_deconv4x4_weights(wq.data(), cout, cin, ocs, N, wpk);
     }
     std::vector<float> biasN(N, 0.f);
-    if (mode == 0) for (int i = 0; i < cout; i++) biasN[i] = bias[i];
+    if (mode == 0 || mode == 4) for (int i = 0; i < cout; i++) biasN[i] = bias[i];
     else for (int p = 0; p < 4; p++) for (int i = 0; i < cout; i++) biasN[p * ocs + i] = bias[i];
     float *d_in = 0, *d_res = 0, *d_bias = 0, *d_biasN = 0, *d_out_tc = 0, *d_out_ref = 0, *d_wT = 0, *d_tmp = 0;
     __half *d_in8 = 0, *d_res8 = 0, *d_out8 = 0, *d_wpk = 0;
-    const size_t out_elems = mode == 0 ? (size_t)cout * hw : (size_t)cout * hw * 4;
+    const size_t out_elems = (mode == 0 || mode == 4) ? (size_t)cout * hw : (size_t)cout * hw * 4;
     cudaMalloc(&d_in, cin * hw * 4); cudaMalloc(&d_in8, cin * hw * 2 * 2); cudaMalloc(&d_bias, cout * 4); cudaMalloc(&d_biasN, N * 4);
     cudaMalloc(&d_out_tc, out_elems * 4); cudaMalloc(&d_out_ref, out_elems * 4); cudaMalloc(&d_tmp, out_elems * 4);
     cudaMalloc(&d_out8, (size_t)cout * hw * 2 * 2); cudaMalloc(&d_wpk, wpk.size() * 2);
@@ -302,23 +303,24 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
     a.wpk = d_wpk; a.bias = d_biasN; a.res = self_res ? d_in8 : d_res8; a.res_plane = (size_t)cout * hw; a.res_split = split;
     a.out = d_out8; a.out_plane = (size_t)cout * hw; a.out_f32 = d_out_tc; a.slope = slope;
     a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.N = N; a.split_in = split; a.split_out = split;
-    a.epi = mode == 0 ? TC_EPI_C8 : TC_EPI_DECONV;
+    a.epi = (mode == 0 || mode == 4) ? TC_EPI_C8 : TC_EPI_DECONV;
+    a.k5 = mode == 4;
     a.res_mode = res ? 1 : 0;
-    a.act_mode = mode == 0 ? 1 : 0;
+    a.act_mode = (mode == 0 || mode == 4) ? 1 : 0;
     a.ocs = ocs; a.ps = ps;
     a.out_planes = planes5 ? 5 : 0;
     int r = launch_tc_conv(a, d_in8, st);
     if (r) { fprintf(stderr, "launch_tc_conv failed: %d\n", r); return RIFE_B200_ERR_INTERNAL; }
-    if (mode == 0) launch_c8_to_planar(d_out8, d_out_tc, cout, h, w, split, st);
+    if (mode == 0 || mode == 4) launch_c8_to_planar(d_out8, d_out_tc, cout, h, w, split, st);
     // fp32 CUDA-core reference
     {
         int ocpad = (cout + 63) / 64 * 64;
         std::vector<float> t;
         ConvArgs c;
         memset(&c, 0, sizeof c);
-        if (mode == 0) {
-            t.assign((size_t)cin * 9 * ocpad, 0.f);
-            for (int oc = 0; oc < cout; oc++) for (int ic = 0; ic < cin; ic++) for (int k = 0; k < 9; k++) t[((size_t)ic * 9 + k) * ocpad + oc] = wq[((size_t)oc * cin + ic) * 9 + k];
+        if (mode == 0 || mode == 4) {
+            t.assign((size_t)cin * kk * ocpad, 0.f);
+            for (int oc = 0; oc < cout; oc++) for (int ic = 0; ic < cin; ic++) for (int k = 0; k < kk; k++) t[((size_t)ic * kk + k) * ocpad + oc] = wq[((size_t)oc * cin + ic) * kk + k];
         } else {
             t.assign((size_t)4 * cin * 4 * ocpad, 0.f);
             for (int p = 0; p < 4; p++) for (int ic = 0; ic < cin; ic++) for (int rr = 0; rr < 2; rr++) for (int cc = 0; cc < 2; cc++) {
@@ -329,10 +331,10 @@ extern "C" int rife_b200_selftest_conv(int gpuid, int mode, int cin, int cout, i
         cudaMalloc(&d_wT, t.size() * 4);
         cudaMemcpy(d_wT, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
         c.in = d_in; c.wT = d_wT; c.bias = d_bias; c.Cin = cin; c.H = h; c.W = w; c.Cout = cout; c.ocpad = ocpad;
-        if (mode == 0) {
-            c.out = d_out_ref; c.OH = h; c.OW = w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 1; c.nparity = 1;
+        if (mode == 0 || mode == 4) {
+            c.out = d_out_ref; c.OH = h; c.OW = w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = mode == 4 ? -2 : -1; c.out_mul = 1; c.nparity = 1;
             c.res = self_res ? d_in : d_res; c.post_act = 2; c.post_p0 = slope;
-            launch_conv(c, 3, 1, st);
+            launch_conv(c, mode == 4 ? 5 : 3, 1, st);
         } else {
             c.out = d_tmp; c.OH = 2 * h; c.OW = 2 * w; c.DH = h; c.DW = w; c.in_off_y = c.in_off_x = -1; c.out_mul = 2; c.nparity = 4;
             launch_conv(c, 2, 1, st);

@@ -100,16 +100,20 @@ int NetRunner::init(const Net* net, std::string& err) {
         if ((L.type == "Convolution" || L.type == "Deconvolution") && L.weight_is_fp16) {
             int cout = L.geti(0, 0), k = L.geti(1, 0);
             bool isconv = L.type == "Convolution";
-            int kk = isconv ? 9 : 16;
+            const bool is5 = isconv && k == 5 && L.geti(11, 5) == 5;
+            int kk = isconv ? (is5 ? 25 : 9) : 16;
             int cin = (int)(L.weight.size() / ((size_t)cout * kk));
-            int N = 0, ocs = 0, s2 = 0, cinp = cin;
+            int N = 0, ocs = 0, s2 = 0, cinp = cin, k5 = 0;
+            // 5x5 s1 p2 (the residual blocks of the rife / HD / UHD / anime flownets): one kernel row per pipeline stage
+            if (is5 && L.geti(3, 1) == 1 && L.geti(4, 0) == 2 && L.geti(2, 1) == 1 && (cout == 48 || cout == 96 || cout == 128 || cout == 192)) { N = cout; k5 = 1; }
             if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout;
             if (isconv && k == 3 && L.geti(3, 1) == 2 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) { N = cout; s2 = 1; if (cin < 16) cinp = 16; }
             if (!isconv) { ocs = (cout + 7) / 8 * 8; N = 4 * ocs; }
             bool nok = isconv ? (N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
             if (nok && cinp % 16 == 0 && cinp >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
                 std::vector<uint16_t> pk;
-                if (isconv && s2) pack_conv3x3s2_weights(L.weight.data(), cout, cin, cinp, N, pk);
+                if (k5) pack_conv5x5_weights(L.weight.data(), cout, cin, N, pk);
+                else if (isconv && s2) pack_conv3x3s2_weights(L.weight.data(), cout, cin, cinp, N, pk);
                 else if (isconv) pack_conv3x3_weights(L.weight.data(), cout, cin, N, pk);
                 else pack_deconv4x4_weights(L.weight.data(), cout, cin, ocs, N, pk);
                 std::vector<float> bN(N, 0.f);
@@ -120,7 +124,7 @@ int NetRunner::init(const Net* net, std::string& err) {
                 if (cudaMalloc(&W.wpk, pk.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
                 cudaMemcpy(W.wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
                 W.biasN = upload(bN, err);
-                W.tcN = N; W.ocs = ocs; W.cin = cin; W.cinp = cinp; W.tc_s2 = s2;
+                W.tcN = N; W.ocs = ocs; W.cin = cin; W.cinp = cinp; W.tc_s2 = s2; W.tc_k5 = k5;
             }
         }
         if (!L.bias.empty()) W.bias = upload(L.bias, err);
@@ -533,6 +537,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
         a.bias = W.biasN;
         a.H = o.h; a.W = o.w; a.Cin = W.cinp; a.Cout = L.geti(0, 0); a.N = W.tcN;
         a.s2 = W.tc_s2;
+        a.k5 = W.tc_k5;
         if (L.type == "Deconvolution") { a.H = x.h; a.W = x.w; }
         a.split_in = plan.split;
         a.num_sms = num_sms;

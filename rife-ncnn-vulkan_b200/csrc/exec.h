@@ -34,7 +34,7 @@ struct DeviceWeights {
     // tensor-core path (tc_conv.cu): packed fp16 weights, bias padded to the GEMM N
     void* wpk = nullptr;
     float* biasN = nullptr;
-    int tcN = 0, ocs = 0, cin = 0, cinp = 0, tc_s2 = 0;
+    int tcN = 0, ocs = 0, cin = 0, cinp = 0, tc_s2 = 0, tc_k5 = 0;
 };
 
 class NetRunner {

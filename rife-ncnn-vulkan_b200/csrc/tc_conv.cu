@@ -186,10 +186,16 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) { return (uint32_t
 // which are not stored.
 template <int N, int MT, int STAGES, int TAPS, int WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, TcConvArgs a) {
-    constexpr int TWP = WIDE ? 128 : 64;          // tile width incl. 1-pixel halo left and right
-    constexpr int TVALID = TWP - 2;
+    // TAPS = 5: a 5x5 stride-1 pad-2 convolution, one KERNEL ROW per pipeline stage.  The K loop runs over (16-channel chunk,
+    // dy): a stage carries the 2*MT image rows that tap row dy reads (no halo rows: the next dy re-loads the rows shifted by
+    // one, from L2) and the weights of its five taps, whose A operands are the slab viewed from start column dx = 0..4.
+    // The tile keeps 60 valid columns (halo 2 left and right).  All 25 taps of a chunk in one stage would need up to 150 KB of
+    // weights per stage (N = 192); a row is 31 KB.
+    constexpr int HALO = TAPS == 5 ? 2 : 1;
+    constexpr int TWP = WIDE ? 128 : 64;          // tile width incl. the halo columns left and right
+    constexpr int TVALID = TWP - 2 * HALO;
     constexpr int RPA = WIDE ? 1 : 2;             // image rows per accumulator
-    constexpr int ROWS = RPA * MT + 2;            // input rows per tile (halo included)
+    constexpr int ROWS = TAPS == 5 ? 2 * MT : RPA * MT + 2;  // input rows per stage (3x3: halo rows included)
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;  // bytes of one plane slab: 2 eight-channel halves
     static_assert(!WIDE || (TAPS == 9 && 3 * N <= 256), "wide tiles: stride-1 convs whose three row taps fit one MMA");
     constexpr int W_BYTES = TAPS * 2 * N * 16;
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     const int tiles_img = a.tiles_x * a.tiles_y;
     const int ntiles = tiles_img * a.batch;  // image-major: tile -> (image, ty, tx)
     const int KCP = a.Cin / 16;                    // K chunks per parity sub-image (all of them for stride 1)
-    const int KC = TAPS == 9 ? KCP : 4 * KCP;
+    const int KC = TAPS == 9 ? KCP : (TAPS == 5 ? 5 * KCP : 4 * KCP);
     const uint32_t dskip = (uint32_t)(a.dbg_skip * KC);  // diagnostics: first recorded pipeline iteration
 
     if (warp == 0 && lane == 0) {
@@ -305,8 +311,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)));
-                    for (int p = 0; p < nplanes; p++)
-                        tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * (WIDE ? 2 : 4), y0 - 1, p * (2 * KC) + 2 * kc, bimg);  // 16 B per pixel = 4 u32 / 2 u64 elements
+                    for (int p = 0; p < nplanes; p++) {
+                        if constexpr (TAPS == 5) tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 2) * 4, y0 - 2 + kc % 5, p * (2 * KCP) + 2 * (kc / 5), bimg);
+                        else tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * (WIDE ? 2 : 4), y0 - 1, p * (2 * KC) + 2 * kc, bimg);  // 16 B per pixel = 4 u32 / 2 u64 elements
+                    }
                     if (!a.wres) bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                     if (dbg && it - dskip < 12u) dbg[1 + it - dskip] = clock64();
                     if (++s == NST) { s = 0; ph ^= 1; }
@@ -371,6 +379,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             const uint32_t accn = acc0 + (uint32_t)(16 * kc);
                             if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
                             else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(accn, a_lo, b_lo, DESC_HI, idesc16, 1u);
+                        }
+                    } else if constexpr (TAPS == 5) {
+#pragma unroll
+                        for (int dx = 0; dx < 5; dx++) {  // the five taps of kernel row kc % 5
+                            const uint32_t b_lo = b_base + (uint32_t)(dx * (2 * N * 16) >> 4);
+                            const uint32_t a_lo = a_base + (uint32_t)dx;
+                            if (nplanes == 2) umma_issue_tap<MT, 2, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
+                            else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                         }
                     } else if constexpr (TAPS == 9) {
                         bool paired = false;
@@ -767,7 +783,7 @@ template <int N, int MT, int STAGES, int TAPS, int WIDE = 0>
 static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t st) {
     TcConvArgs a = a_in;
     constexpr int TWP = WIDE ? 128 : 64;
-    constexpr int ROWS = (WIDE ? 1 : 2) * MT + 2;
+    constexpr int ROWS = TAPS == 5 ? 2 * MT : (WIDE ? 1 : 2) * MT + 2;
     constexpr int A_PLANE = 2 * ROWS * TWP * 16;
     constexpr int W_BYTES = TAPS * 2 * N * 16;
     const int nplanes = a.split_in ? 2 : 1;
@@ -776,7 +792,7 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     const size_t ident_bytes = (size_t)2 * (2 * N - 16) * 16;
     // resident weights (stride-1 kernels): the whole packed layer next to activation-only stages, when it fits
     static const bool wres_ok = !(getenv("RIFE_B200_WRES") && atoi(getenv("RIFE_B200_WRES")) == 0);
-    const size_t w_all = (size_t)(a.Cin / 16) * W_BYTES;
+    const size_t w_all = (size_t)(a.Cin / 16) * W_BYTES * (TAPS == 5 ? 5 : 1);
     const size_t budget = 227 * 1024;
     const size_t stage_a = (size_t)((A_PLANE * nplanes + 1023) & ~1023), stage_aw = (size_t)((A_PLANE * nplanes + W_BYTES + 1023) & ~1023);
     // resident weights need at least STAGES activation-only stages next to the whole layer
@@ -819,6 +835,10 @@ static int launch_n(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st)
     if constexpr (N == 64) {  // the instance tc_wide_enabled() admits
         if (a.wide) return launch_t<N, MT, STAGES, 9, 1>(a, tm, st);
     }
+    if constexpr (N == 48 || N == 96 || N == 128 || N == 192) {  // the widths of the 5x5 residual blocks (rife / HD / UHD / anime flownets)
+        if (a.k5) return launch_t<N, MT, 2, 5>(a, tm, st);
+    }
+    if (a.k5) return -6;
     return a.s2 ? launch_t<N, MT, STAGES, 4>(a, tm, st) : launch_t<N, MT, STAGES, 9>(a, tm, st);
 }
 
@@ -830,8 +850,9 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     const int MT = tc_conv_tile_rows(a.N) / 2;
     // wide tiles (one-row accumulators of 128 pixels, MT rows x 126 columns): stride-1 convolutions whose weights were packed
     // for them (tc_wide_enabled), C8 output in plain (not space-to-depth) form
-    a.wide = (!a.s2 && a.epi == TC_EPI_C8 && !a.out_s2d && tc_wide_enabled(a.N)) ? 1 : 0;
-    const int TWP = a.wide ? 128 : 64, TVALID = TWP - 2, tile_rows = a.wide ? MT : 2 * MT;
+    a.wide = (!a.s2 && !a.k5 && a.epi == TC_EPI_C8 && !a.out_s2d && tc_wide_enabled(a.N)) ? 1 : 0;
+    if (a.k5 && (a.s2 || a.epi != TC_EPI_C8)) return -4;
+    const int TWP = a.wide ? 128 : 64, TVALID = TWP - (a.k5 ? 4 : 2), tile_rows = a.wide ? MT : 2 * MT;
     a.tiles_x = (a.W + TVALID - 1) / TVALID;
     a.tiles_y = (a.H + tile_rows - 1) / tile_rows;
     if (!a.num_sms) a.num_sms = 148;
@@ -844,10 +865,10 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     if (a.res_mode == 3) return -9;  // internal value, selected below
     // residual == the conv's own input (the ResConv blocks): let the tensor core add it (identity tap, see the kernel)
     static const bool ident_ok = !(getenv("RIFE_B200_RES_IDENT") && atoi(getenv("RIFE_B200_RES_IDENT")) == 0);
-    if (ident_ok && a.res_mode == 1 && a.epi == TC_EPI_C8 && !a.s2 && a.res == (const __half*)in && a.Cin == a.N && a.Cout == a.N && a.N <= 128 && (!a.res_split) == (!a.split_in) &&
+    if (ident_ok && a.res_mode == 1 && a.epi == TC_EPI_C8 && !a.s2 && !a.k5 && a.res == (const __half*)in && a.Cin == a.N && a.Cout == a.N && a.N <= 128 && (!a.res_split) == (!a.split_in) &&
         (!a.split_in || a.res_plane == (size_t)a.Cin * a.H * a.W) && (a.batch == 1 || a.res_bstride == a.in_bstride))
         a.res_mode = 3;
-    a.pair = (!a.s2 && !a.wide && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
+    a.pair = (!a.s2 && !a.wide && !a.k5 && tc_pair_enabled(a.N)) ? 1 : 0;  // the weights were packed accordingly (pack_*_weights)
     if (tc_pair_mode() & 2) a.pair |= 2;  // narrow identity tap for the self-residual layers (independent of the weight layout)
     const size_t img_bytes = (size_t)nplanes * cgroups * a.H * a.W * 16;
     if (a.batch > 1 && a.in_bstride * 2 < img_bytes) return -8;
@@ -856,7 +877,7 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     const int epp = a.wide ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)a.W * epp, (cuuint64_t)a.H, (cuuint64_t)nplanes * cgroups, (cuuint64_t)a.batch};
     cuuint64_t strides[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.H * a.W * 16, a.batch > 1 ? (cuuint64_t)a.in_bstride * 2 : (cuuint64_t)img_bytes};
-    cuuint32_t box[4] = {(cuuint32_t)(TWP * epp), (cuuint32_t)(tile_rows + 2), 2, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(TWP * epp), (cuuint32_t)(a.k5 ? tile_rows : tile_rows + 2), 2, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tm, a.wide ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -993,6 +1014,19 @@ void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<
     // paired: -1 = what the launcher will assume for a stride-1 conv of this N; 0 plain; 1 paired; 2 wide
     if (paired == 2 || (paired < 0 && tc_wide_enabled(N))) { if (3 * N <= 256) to_wide_layout(out, cin / 16, N); }
     else if (paired < 0 ? tc_pair_enabled(N) : (paired != 0 && 2 * N <= 256)) to_paired_layout(out, cin / 16, N);
+}
+// conv 5x5 stride 1: w[oc][ic][5][5] fp32 (fp16-exact) -> wpk[kc][dy][dx][half][n][8]: one kernel row (five taps) per pipeline stage
+void pack_conv5x5_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out) {
+    out.assign((size_t)(cin / 16) * 25 * 2 * N * 8, 0);
+    for (int kc = 0; kc < cin / 16; kc++)
+        for (int tap = 0; tap < 25; tap++)
+            for (int hf = 0; hf < 2; hf++)
+                for (int n = 0; n < cout; n++)
+                    for (int j = 0; j < 8; j++) {
+                        int ic = kc * 16 + hf * 8 + j;
+                        __half h = __float2half_rn(w[((size_t)n * cin + ic) * 25 + tap]);
+                        out[((((size_t)kc * 25 + tap) * 2 + hf) * N + n) * 8 + j] = __half_as_ushort(h);
+                    }
 }
 // conv 3x3 stride 2: w[oc][ic][3][3] -> wpk[4 parities][cinp/16][4 slots][2][N][8]; parity (py,px) of the space-to-depth
 // input, slot (iy*2+ix) <-> tap dy = py ? 2*iy : 1, dx = px ? 2*ix : 1; input channels zero padded to cinp

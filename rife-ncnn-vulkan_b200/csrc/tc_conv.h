@@ -29,6 +29,7 @@ struct TcConvArgs {
     int out_planes;         // deconv + PixelShuffle: store only the first out_planes planes (0 = all)
     int batch;              // images per launch (0 / 1 = single); image b lives at base + b * *_bstride
     size_t in_bstride, res_bstride, out_bstride, outf_bstride;  // elements of the respective tensors
+    int k5;                 // 5x5 stride-1 pad-2 convolution (weights from pack_conv5x5_weights)
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
@@ -57,6 +58,7 @@ void launch_c8_to_planar(const __half* in, float* out, int C, int H, int W, int 
 
 // paired: -1 = what the launcher will assume for this N (tc_wide_enabled / tc_pair_enabled), 0 plain / 1 paired / 2 wide = explicit (diagnostics)
 void pack_conv3x3_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out, int paired = -1);
+void pack_conv5x5_weights(const float* w, int cout, int cin, int N, std::vector<uint16_t>& out);
 void pack_conv3x3s2_weights(const float* w, int cout, int cin, int cinp, int N, std::vector<uint16_t>& out);
 void pack_deconv4x4_weights(const float* w, int cout, int cin, int ocs, int N, std::vector<uint16_t>& out, int paired = -1);
 

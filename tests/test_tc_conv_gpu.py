@@ -106,3 +106,35 @@ def test_conv3x3_wide_tiles(pkg, h, w, self_res, split):
     o_tc, o_ref = pkg.selftest_conv(0, x, wgt, b, res=x if self_res else res, slope=0.2, split=bool(split))
     mx, tol, bad = _check(o_tc, o_ref, split)
     assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
+@pytest.mark.parametrize("c", [48, 96, 128, 192])
+@pytest.mark.parametrize("split", [1, 0])
+def test_conv5x5_row_stages(pkg, c, split):
+    """5x5 stride-1 pad-2 convolution (the residual blocks of the rife / HD / UHD / anime flownets) on the tensor cores: one
+    kernel row (five shifted views of 2*MT image rows) per pipeline stage; two column tiles (60 + 10), ragged last row tile."""
+    h, w = 21, 70
+    rng = np.random.default_rng(c)
+    x = rng.standard_normal((c, h, w), dtype=np.float32)
+    wgt = (rng.standard_normal((c, c, 25), dtype=np.float32) / np.sqrt(c * 25)).astype(np.float32)
+    b = rng.standard_normal(c).astype(np.float32) * 0.1
+    res = rng.standard_normal((c, h, w), dtype=np.float32)
+    o_tc, o_ref = pkg.selftest_conv(4, x, wgt, b, res=res, slope=0.2, split=bool(split))
+    mx, tol, bad = _check(o_tc, o_ref, split)
+    assert len(bad) == 0, "max err %g (tol %g); first bad idx %s of %d" % (mx, tol, bad[:5].tolist(), len(bad))
+
+
+def test_conv5x5_single_taps(pkg):
+    """One non-zero tap at a time localises a wrong view (row stage dy / column shift dx)."""
+    c, h, w = 48, 10, 64
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((c, h, w), dtype=np.float32)
+    wgt = (rng.standard_normal((c, c, 25), dtype=np.float32) / np.sqrt(c)).astype(np.float32)
+    report = []
+    for tap in (0, 4, 7, 12, 20, 24):
+        wt = np.zeros_like(wgt)
+        wt[:, :, tap] = wgt[:, :, tap]
+        o_tc, o_ref = pkg.selftest_conv(4, x, wt, np.zeros(c, np.float32), res=None, slope=1.0, split=True)
+        mx, tol, bad = _check(o_tc, o_ref, 1)
+        report.append((tap, mx, len(bad)))
+    assert all(n == 0 for _, _, n in report), report
