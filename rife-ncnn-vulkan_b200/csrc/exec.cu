@@ -95,8 +95,9 @@ int NetRunner::init(const Net* net, std::string& err) {
         } else if (L.type == "InnerProduct") {
             W.wT = upload(L.weight, err);
         }
-        // tensor-core eligibility (tc_conv.cu): 3x3 s1 p1 conv with Cin % 16 == 0 and N in {32,64,96,128,192};
-        // deconv 4x4 s2 p1 re-expressed as a 3x3 conv with N = 4 * ocs in {32, 96}
+        // tensor-core eligibility (tc_conv.cu): 3x3 s1 / s2 p1 conv with Cin % 16 == 0 (narrow stride-2 inputs are padded to 16) and
+        // N in {32,48,64,96,128,192}, wider ones (256 / 384 / 512) as slices of 128; 5x5 s1 p2 with N in {48,96,128,192};
+        // deconv 4x4 s2 p1 re-expressed as a 3x3 conv with N = 4 * ocs in {32, 96}, wider ones as slices of 16 channels
         if ((L.type == "Convolution" || L.type == "Deconvolution") && L.weight_is_fp16) {
             int cout = L.geti(0, 0), k = L.geti(1, 0);
             bool isconv = L.type == "Convolution";
@@ -109,22 +110,37 @@ int NetRunner::init(const Net* net, std::string& err) {
             if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout;
             if (isconv && k == 3 && L.geti(3, 1) == 2 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) { N = cout; s2 = 1; if (cin < 16) cinp = 16; }
             if (!isconv) { ocs = (cout + 7) / 8 * 8; N = 4 * ocs; }
-            bool nok = isconv ? (N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
+            // Layers wider than one accumulator set run as output-channel slices: convolutions with 256 / 384 / 512 output
+            // channels as slices of 128 (the context / fusion pyramids of the 3-net families), deconvolutions with 32 .. 256
+            // output channels as slices of 16 (4 parities x 16 = 64 GEMM columns; the deconv epilogue holds a row of them in registers)
+            int nchunks = 1, cchunk = cout;  // output channels per slice
+            if (isconv && !k5 && N > 192 && N % 128 == 0 && N <= 512) { nchunks = N / 128; cchunk = 128; N = 128; }
+            if (!isconv && !(N == 32 || N == 96) && cout % 16 == 0 && cout >= 32 && cout <= 256) { nchunks = cout / 16; cchunk = 16; ocs = 16; N = 64; }
+            bool nok = isconv ? (N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96 || N == 64);
             if (nok && cinp % 16 == 0 && cinp >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
-                std::vector<uint16_t> pk;
-                if (k5) pack_conv5x5_weights(L.weight.data(), cout, cin, N, pk);
-                else if (isconv && s2) pack_conv3x3s2_weights(L.weight.data(), cout, cin, cinp, N, pk);
-                else if (isconv) pack_conv3x3_weights(L.weight.data(), cout, cin, N, pk);
-                else pack_deconv4x4_weights(L.weight.data(), cout, cin, ocs, N, pk);
-                std::vector<float> bN(N, 0.f);
-                if (!L.bias.empty()) {
-                    if (isconv) for (int i = 0; i < cout; i++) bN[i] = L.bias[i];
-                    else for (int p = 0; p < 4; p++) for (int i = 0; i < cout; i++) bN[p * ocs + i] = L.bias[i];
+                std::vector<uint16_t> pk_all;
+                size_t chunk_elems = 0;
+                for (int ch = 0; ch < nchunks; ch++) {
+                    std::vector<uint16_t> pk;
+                    const float* wc = L.weight.data() + (size_t)ch * cchunk * cin * kk;  // weights are [oc][ic][kk]: a slice of output channels is contiguous
+                    if (k5) pack_conv5x5_weights(wc, cchunk, cin, N, pk);
+                    else if (isconv && s2) pack_conv3x3s2_weights(wc, cchunk, cin, cinp, N, pk);
+                    else if (isconv) pack_conv3x3_weights(wc, cchunk, cin, N, pk);
+                    else pack_deconv4x4_weights(wc, cchunk, cin, ocs, N, pk);
+                    chunk_elems = pk.size();
+                    pk_all.insert(pk_all.end(), pk.begin(), pk.end());
                 }
-                if (cudaMalloc(&W.wpk, pk.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
-                cudaMemcpy(W.wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice);
+                std::vector<float> bN((size_t)N * nchunks, 0.f);
+                if (!L.bias.empty()) {
+                    for (int ch = 0; ch < nchunks; ch++) {
+                        if (isconv) for (int i = 0; i < cchunk; i++) bN[(size_t)ch * N + i] = L.bias[ch * cchunk + i];
+                        else for (int p = 0; p < 4; p++) for (int i = 0; i < cchunk; i++) bN[(size_t)ch * N + p * ocs + i] = L.bias[ch * cchunk + i];
+                    }
+                }
+                if (cudaMalloc(&W.wpk, pk_all.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
+                cudaMemcpy(W.wpk, pk_all.data(), pk_all.size() * 2, cudaMemcpyHostToDevice);
                 W.biasN = upload(bN, err);
-                W.tcN = N; W.ocs = ocs; W.cin = cin; W.cinp = cinp; W.tc_s2 = s2; W.tc_k5 = k5;
+                W.tcN = N; W.ocs = ocs; W.cin = cin; W.cinp = cinp; W.tc_s2 = s2; W.tc_k5 = k5; W.nchunks = nchunks; W.chunk_elems = chunk_elems;
             }
         }
         if (!L.bias.empty()) W.bias = upload(L.bias, err);
@@ -255,11 +271,11 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             if (L.type == "Convolution") {
                 bool ok = own_act == 0 || (own_act == 2 && s.fused_act_layer < 0 && s.fused_add_blob < 0);
                 if (ok) s.kind = 1;
-            } else if (s.fused_act_layer < 0 && (own_act == 0 || own_act == 4)) {
-                s.kind = 1;
+            } else if ((own_act == 0 || own_act == 4) && (s.fused_act_layer < 0 || own_act == 0)) {
+                s.kind = 1;  // (a PReLU / leaky fused behind the deconvolution is applied by its epilogue)
                 int c1 = sole_consumer(L.tops[0]);
                 if (c1 >= 0 && net.layers[c1].type == "PixelShuffle" && net.layers[c1].geti(0, 1) == 2 && net.layers[c1].geti(1, 0) == 0 &&
-                    L.geti(0, 0) % 4 == 0 && plan.external_slot[net.layers[c1].tops[0]] < 0) {
+                    L.geti(0, 0) % 4 == 0 && plan.external_slot[net.layers[c1].tops[0]] < 0 && (*dwp_)[l].nchunks == 1 && s.fused_act_layer < 0) {
                     s.fused_ps_layer = c1;
                     s.out_blob = net.layers[c1].tops[0];
                     skipped[c1] = 1;
@@ -541,7 +557,8 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
         if (L.type == "Deconvolution") { a.H = x.h; a.W = x.w; }
         a.split_in = plan.split;
         a.num_sms = num_sms;
-        if (L.type == "Convolution") {
+        const bool isconv = L.type == "Convolution";
+        if (isconv) {
             a.epi = TC_EPI_C8;
             a.out = c8ptr(s.out_blob);
             a.out_plane = o.count();
@@ -558,12 +575,6 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
                 a.act_mode = 1;
                 a.slope = ap && !ap->af.empty() ? ap->af[0] : 0.f;
             }
-            if (s.fused_act_layer >= 0) {
-                const Layer& A = net.layers[s.fused_act_layer];
-                if (A.type == "ReLU") { a.act_mode = 1; a.slope = A.getf(0, 0.f); }
-                else if (A.slope.size() == 1) { a.act_mode = 1; a.slope = A.slope[0]; }
-                else { a.act_mode = 2; a.prelu = (*dwp_)[s.fused_act_layer].slope; }
-            }
         } else {
             a.epi = TC_EPI_DECONV;
             a.out_f32 = o.p;
@@ -571,8 +582,33 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
             a.ps = s.fused_ps_layer >= 0 ? 2 : 1;
             a.act_mode = L.geti(9, 0) == 4 ? 3 : 0;
         }
-        int r = launch_tc_conv(a, c8ptr(L.bottoms[0]), st);
-        if (r) { err = "launch_tc_conv failed for " + L.name; return -32; }
+        if (s.fused_act_layer >= 0) {
+            const Layer& A = net.layers[s.fused_act_layer];
+            if (A.type == "ReLU") { a.act_mode = 1; a.slope = A.getf(0, 0.f); }
+            else if (A.slope.size() == 1) { a.act_mode = 1; a.slope = A.slope[0]; }
+            else { a.act_mode = 2; a.prelu = (*dwp_)[s.fused_act_layer].slope; }
+        }
+        // output-channel slices (W.nchunks > 1): each launch writes W.tcN GEMM columns' worth of channels of the same tensor
+        const int cchunk = isconv ? W.tcN : W.ocs;  // channels per slice
+        for (int ch = 0; ch < W.nchunks; ch++) {
+            TcConvArgs b = a;
+            if (W.nchunks > 1) {
+                b.wpk = a.wpk + (size_t)ch * W.chunk_elems;
+                b.bias = a.bias + (size_t)ch * W.tcN;
+                b.Cout = cchunk;
+                if (a.prelu) b.prelu = a.prelu + (size_t)ch * cchunk;
+                if (isconv) {
+                    const size_t hw = (size_t)o.h * o.w, cg_stride = a.out_s2d ? hw / 4 : hw;
+                    b.out_cgroups = o.c / 8;
+                    b.out = a.out + (size_t)ch * (cchunk / 8) * cg_stride * 8;
+                    if (a.res) b.res = a.res + (size_t)ch * (cchunk / 8) * hw * 8;
+                } else {
+                    b.out_f32 = a.out_f32 + (size_t)ch * cchunk * o.h * o.w;
+                }
+            }
+            int r = launch_tc_conv(b, c8ptr(L.bottoms[0]), st);
+            if (r) { err = "launch_tc_conv failed for " + L.name; return -32; }
+        }
         return 0;
     }
     const Layer& L = net.layers[s.layer];

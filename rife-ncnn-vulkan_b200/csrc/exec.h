@@ -35,6 +35,8 @@ struct DeviceWeights {
     void* wpk = nullptr;
     float* biasN = nullptr;
     int tcN = 0, ocs = 0, cin = 0, cinp = 0, tc_s2 = 0, tc_k5 = 0;
+    int nchunks = 1;         // wide layers run as nchunks launches of tcN GEMM columns each (output-channel slices)
+    size_t chunk_elems = 0;  // packed fp16 elements per chunk
 };
 
 class NetRunner {

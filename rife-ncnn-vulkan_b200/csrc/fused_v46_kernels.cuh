@@ -64,10 +64,21 @@ struct Frame {
     int wp;
 };
 __device__ __forceinline__ void px3(const Frame& f, int x, int y, float* o) {
+#if defined(__CUDA_ARCH__) && !defined(RIFE_FUSED_NO_PRMT)
+    // u8 -> float without the quarter-rate conversion pipe (24 I2F.U8 per pixel made these kernels conversion-bound):
+    // byte b dropped into the mantissa of 2^23 gives the float 2^23 + b exactly (one PRMT); then
+    // fma(2^23 + b, r, -2^23 * r) = b * r rounded once -- bit-identical to (float)b * r, since 2^23 * r is exact.
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(f.p + (size_t)y * f.wp + x));
+    constexpr float r = 1 / 255.f, off = -8388608.f * r;
+    o[0] = __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)), r, off);
+    o[1] = __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)), r, off);
+    o[2] = __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)), r, off);
+#else
     const uchar4 q = __ldg(f.p + (size_t)y * f.wp + x);
     o[0] = (float)q.x * (1 / 255.f);
     o[1] = (float)q.y * (1 / 255.f);
     o[2] = (float)q.z * (1 / 255.f);
+#endif
 }
 // bilinear tap of the three colour planes (interp.cpp:92-175: horizontal pass, then vertical)
 __device__ __forceinline__ void bilerp3(const Frame& f, int sy, int sx, float a0, float a1, float b0, float b1, float* o) {

@@ -250,8 +250,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < N; i += NTHREADS)
-        slope_s[i] = (a.act_mode == 1 ? a.slope : ((a.act_mode == 2 && i < a.Cout) ? a.prelu[i] : 1.f)) - 1.f;  // stored as slope - 1
+    for (int i = threadIdx.x; i < N; i += NTHREADS) {
+        // conv: GEMM column = output channel; deconv: column = parity * ocs + channel
+        const int ch = a.epi == TC_EPI_DECONV ? (a.ocs > 0 ? i % a.ocs : i) : i;
+        slope_s[i] = (a.act_mode == 1 ? a.slope : ((a.act_mode == 2 && ch < a.Cout) ? a.prelu[ch] : 1.f)) - 1.f;  // stored as slope - 1
+    }
     for (int i = threadIdx.x; i < 2 * 128 * 8; i += NTHREADS) ones[i] = __float2half_rn((i < 128 * 8 && (i & 7) < 3) ? 1.f : 0.f);
     for (int i = threadIdx.x; i < 2 * N; i += NTHREADS) {
         const int n = i % N, hf = i / N;
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 const int yb = y0 + yrow;  // row of accumulator 0; accumulator m is RPA rows further down each
                 const size_t cg_stride = !s2d ? HW : (HW >> 2);
                 const size_t pix0 = !s2d ? (size_t)yb * a.W + x : (size_t)(yb >> 1) * (a.W >> 1) + (x >> 1);
-                const size_t cg_base = !s2d ? 0 : (size_t)((yb & 1) * 2 + (x & 1)) * (a.Cout / 8);
+                const size_t cg_base = !s2d ? 0 : (size_t)((yb & 1) * 2 + (x & 1)) * a.out_cgroups;
                 __half* const obase = out_b + (cg_base * cg_stride + pix0) * 8;
                 static_assert(!WIDE || RPA == 1, "");
                 // (space-to-depth output: rows alternate between the two row-parity sub-images, so it needs 2-row accumulators)
@@ -521,6 +524,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const int m = blk / NCBL, cb = blk - m * NCBL;
                     if (!(xvalid && yb + RPA * m < a.H)) return;
                     __half* op = obase + m * mstep + cb * cbstep;
+                    if constexpr (WIDE) {
+                        if (s2d) {  // one-row accumulators: consecutive accumulators alternate between the two row-parity sub-images
+                            const int y = yb + m;
+                            op = out_b + (((size_t)((y & 1) * 2 + (x & 1)) * a.out_cgroups) * cg_stride + (size_t)(y >> 1) * (a.W >> 1) + (x >> 1)) * 8 + cb * cbstep;
+                        }
+                    }
 #pragma unroll
                     for (int g = 0; g < CBL / 8; g++) {
                         uint32_t hw_[4], lw_[4];
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + m * N + cb * CB;
                     const size_t pix = !a.out_s2d ? (size_t)y * a.W + x : (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
                     const size_t cg_stride = !a.out_s2d ? HW : (HW >> 2);
-                    const size_t cg_base = !a.out_s2d ? 0 : (size_t)((y & 1) * 2 + (x & 1)) * (a.Cout / 8);
+                    const size_t cg_base = !a.out_s2d ? 0 : (size_t)((y & 1) * 2 + (x & 1)) * a.out_cgroups;
 #pragma unroll
                     for (int c = 0; c < CB / 16; c++) {
                         uint32_t r[16];
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 if constexpr (N <= 96) {
                 const int r_ = a.ps;
                 const int OH = a.H * 2 * r_, OW = a.W * 2 * r_;
-                if (N == 96 && r_ == 2 && a.act_mode != 3 && a.out_planes == 5) {
+                if (N == 96 && r_ == 2 && a.act_mode == 0 && a.out_planes == 5) {
                     // the IFNet flow head (24 channels -> PixelShuffle(2) -> 4 flow + 1 mask planes, the sixth plane is never
                     // read): per (accumulator m, output-row parity py) 2 x 20 of the 48 columns are needed; they go out
                     // as 10 coalesced 16-byte stores straight from the loaded registers.  The bias is already in the accumulator.
@@ -719,6 +728,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             for (int j = 0; j < 16; j++) {
                                 float val = __uint_as_float(r[j]);  // bias: already in the accumulator
                                 if (a.act_mode == 3) val = 1.f / (1.f + expf(-fminf(fmaxf(val, -88.3762626647949f), 88.3762626647949f)));
+                                else if (a.act_mode != 0) val = fmaf(fminf(val, 0.f), slope_s[py * NH + c0 + j], val);  // leaky / PReLU: v + min(v, 0) * (slope - 1)
                                 v[c0 + j] = val;
                             }
                         }
@@ -849,8 +859,8 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     const int nplanes = a.split_in ? 2 : 1;
     const int MT = tc_conv_tile_rows(a.N) / 2;
     // wide tiles (one-row accumulators of 128 pixels, MT rows x 126 columns): stride-1 convolutions whose weights were packed
-    // for them (tc_wide_enabled), C8 output in plain (not space-to-depth) form
-    a.wide = (!a.s2 && !a.k5 && a.epi == TC_EPI_C8 && !a.out_s2d && tc_wide_enabled(a.N)) ? 1 : 0;
+    // for them (tc_wide_enabled)
+    a.wide = (!a.s2 && !a.k5 && a.epi == TC_EPI_C8 && tc_wide_enabled(a.N)) ? 1 : 0;  // must equal the packers' choice (pack_conv3x3_weights)
     if (a.k5 && (a.s2 || a.epi != TC_EPI_C8)) return -4;
     const int TWP = a.wide ? 128 : 64, TVALID = TWP - (a.k5 ? 4 : 2), tile_rows = a.wide ? MT : 2 * MT;
     a.tiles_x = (a.W + TVALID - 1) / TVALID;
@@ -862,6 +872,7 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
     const int cgroups = (a.s2 ? 4 : 1) * (a.Cin / 8);
     if (a.out_s2d && ((a.H | a.W) & 1)) return -7;
     if (a.batch < 1) a.batch = 1;
+    if (a.out_cgroups <= 0) a.out_cgroups = a.Cout / 8;  // a launch that writes a channel slice of a wider tensor sets it to the tensor's groups
     if (a.res_mode == 3) return -9;  // internal value, selected below
     // residual == the conv's own input (the ResConv blocks): let the tensor core add it (identity tap, see the kernel)
     static const bool ident_ok = !(getenv("RIFE_B200_RES_IDENT") && atoi(getenv("RIFE_B200_RES_IDENT")) == 0);

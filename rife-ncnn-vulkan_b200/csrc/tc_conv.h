@@ -32,6 +32,7 @@ struct TcConvArgs {
     int k5;                 // 5x5 stride-1 pad-2 convolution (weights from pack_conv5x5_weights)
     int s2;                 // stride-2 conv: `in` is the space-to-depth tensor (4 sub-images of H x W, Cin channels each)
     int out_s2d;            // write the C8 output in space-to-depth form (H, W even)
+    int out_cgroups;        // 8-channel groups of the output TENSOR (0 = Cout / 8); larger when this launch writes a channel slice of it
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
@@ -50,7 +51,7 @@ int tc_conv_tile_rows(int N);
 constexpr int TC_PAIR_DEFAULT = 3;
 int tc_pair_mode();
 bool tc_pair_enabled(int N);
-constexpr int TC_WIDE_DEFAULT = 1;
+constexpr int TC_WIDE_DEFAULT = 0;  // measured slower than the paired 2-row form (profiles/README.md, round 2 session 2): 739 vs 687 us per 8 launches
 bool tc_wide_enabled(int N);
 
 void launch_planar_to_c8(const float* in, __half* out, int C, int H, int W, int split, cudaStream_t st, int Cpad = 0, int s2d = 0);
