@@ -85,7 +85,10 @@ int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned ch
  * "frame_cache" (0/1, default 0): input frames uploaded by rife_b200_process / _process_batch stay on the device and are
  *   found again by host pointer in later calls (pair (k, k+1) then uploads only frame k+1).  The caller must not modify
  *   or free-and-reuse a frame buffer it has handed in until rife_b200_forget_frames() or "frame_cache" = 0.
- *   Within one call a frame shared by several pairs is always uploaded once. */
+ *   Within one call a frame shared by several pairs is always uploaded once.
+ * "stage_pageable" (0/1, default 1): rife_b200_process calls that arrive with pageable buffers (what the reference CLI passes)
+ *   copy their frames through a pinned slot in the CALLING thread, so concurrent callers copy in parallel and the combined
+ *   batch runs on asynchronous DMA only; ignored while "frame_cache" is on. */
 int rife_b200_set_option(rife_b200_t* handle, const char* key, int value);
 /* reads back "precision", "lanes", "fast" (requested) and "fast_active" (1 when the fused rife-v4.6 path passed its
  * load-time self-check against the generic executor and is the one process() runs) */

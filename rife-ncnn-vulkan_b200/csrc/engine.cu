@@ -56,6 +56,7 @@ Engine::~Engine() {
     // borrowers first, the weight-owning lane 0 last
     for (size_t i = lanes_.size(); i-- > 0;) { lanes_[i]->release(); delete lanes_[i]; }
     for (auto& b : out_u8_) b.release();
+    for (auto& sl : stage_) if (sl.p) cudaFreeHost(sl.p);
     for (auto& f : frames_) { f.buf.release(); if (f.read_done) cudaEventDestroy(f.read_done); }
     for (int i = 0; i < kSlots; i++) {
         if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
@@ -193,6 +194,7 @@ void Engine::publish() {
     snap_combine_.store(combine_ && loaded_ ? 1 : 0, std::memory_order_relaxed);
     snap_fast_.store(loaded_ && fast_usable() ? 1 : 0, std::memory_order_relaxed);
     snap_batch_.store(batch_, std::memory_order_relaxed);
+    snap_stage_.store(stage_pageable_ && !frame_cache_ ? 1 : 0, std::memory_order_relaxed);
     snap_lanes_.store((int)lanes_.size(), std::memory_order_release);
 }
 
@@ -258,6 +260,7 @@ int Engine::set_option(const std::string& key, int value) {
         for (Lane* L : lanes_) if (L->fast) L->fast->set_ktime(value);
         return 0;
     }
+    if (key == "stage_pageable") { stage_pageable_ = value != 0; return 0; }
     if (key == "batch") { batch_ = value < 0 ? 0 : (value > V46_MAX_BATCH ? V46_MAX_BATCH : value); return 0; }
     if (key == "async") { async_ = value != 0; return 0; }
     if (key == "combine") { combine_ = value != 0; return 0; }
@@ -292,6 +295,7 @@ int Engine::get_option(const std::string& key, int* value) {
     else if (key == "head_pack") *value = head_pack_;
     else if (key == "bgr") *value = bgr_;
     else if (key == "frame_cache") *value = frame_cache_;
+    else if (key == "stage_pageable") *value = stage_pageable_;
     else if (key == "frame_cache_hits") *value = (int)frame_hits_;
     else if (key == "combined_batches") *value = (int)combiner_.batches();
     else if (key == "combined_requests") *value = (int)combiner_.requests();
@@ -398,11 +402,56 @@ int Engine::run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t
     return 0;
 }
 
+uint8_t* Engine::stage_acquire(size_t bytes, int* idx) {
+    std::lock_guard<std::mutex> lk(stage_mu_);
+    int free_i = -1;
+    for (size_t i = 0; i < stage_.size(); i++)
+        if (!stage_[i].busy) { if (stage_[i].cap >= bytes) { stage_[i].busy = true; *idx = (int)i; return stage_[i].p; } if (free_i < 0) free_i = (int)i; }
+    if (free_i < 0) {
+        if (stage_.size() >= 64) return nullptr;  // more concurrent callers than that: let the driver stage
+        stage_.emplace_back();
+        free_i = (int)stage_.size() - 1;
+    }
+    StageSlot& s = stage_[free_i];
+    if (s.p) cudaFreeHost(s.p);
+    s.p = nullptr;
+    s.cap = 0;
+    cudaSetDevice(gpuid_);
+    if (cudaHostAlloc((void**)&s.p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); s.p = nullptr; return nullptr; }
+    s.cap = bytes;
+    s.busy = true;
+    *idx = free_i;
+    return s.p;
+}
+void Engine::stage_release(int idx) {
+    std::lock_guard<std::mutex> lk(stage_mu_);
+    stage_[idx].busy = false;
+}
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 int Engine::process_host(const uint8_t* in0, const uint8_t* in1, int w, int h, float t, uint8_t* out) {
     const uint8_t* a[1] = {in0};
     const uint8_t* b[1] = {in1};
     uint8_t* o[1] = {out};
     if (!in0 || !in1 || !out) { set_error("bad argument"); return -1; }
+    if (w > 0 && h > 0 && t != 0.f && t != 1.f && snap_stage_.load(std::memory_order_relaxed) && (is_pageable(in0) || is_pageable(in1) || is_pageable(out))) {
+        // pageable caller memory: stage through a pinned slot in THIS thread (see engine.h), then run the same path on the slot
+        const size_t nb = (size_t)w * h * 3;
+        int idx = -1;
+        if (uint8_t* sl = stage_acquire(3 * nb, &idx)) {
+            memcpy(sl, in0, nb);
+            memcpy(sl + nb, in1, nb);
+            const int r = process_host(sl, sl + nb, w, h, t, sl + 2 * nb);
+            if (!r) memcpy(out, sl + 2 * nb, nb);
+            stage_release(idx);
+            return r;
+        }
+    }
     // The reference's CLI calls process() from several proc threads on one object (src/main.cpp:346-366): requests that
     // arrive while another is being served are executed together as one lock-step batch instead of one after the other.
     // Decided from a lock-free snapshot: the leader of a running batch holds mu_, followers must still be able to queue.

@@ -131,6 +131,19 @@ private:
     int frame_cache_ = 0;
     unsigned long long frame_hits_ = 0;
     FrameEntry* frame_lookup(const uint8_t* host, size_t nb, FrameEntry* const* cur, int ncur, bool* hit);
+    // Pinned staging for process() calls that arrive with pageable buffers (what the reference CLI passes: stb_image / malloc
+    // memory, src/main.cpp:140-187): every caller thread copies its own frames into a pinned slot BEFORE it queues, and its result
+    // out of the slot afterwards, so the copies of concurrent callers run in parallel on their own cores and the thread that
+    // executes the combined batch only issues asynchronous DMA (a pageable cudaMemcpyAsync is staged by the driver, serially,
+    // in that one thread).  Option "stage_pageable" (default 1; ignored while "frame_cache" is on: slots are reused, pointers
+    // would lie).
+    struct StageSlot { uint8_t* p = nullptr; size_t cap = 0; bool busy = false; };
+    std::vector<StageSlot> stage_;
+    std::mutex stage_mu_;
+    int stage_pageable_ = 1;
+    std::atomic<int> snap_stage_{1};
+    uint8_t* stage_acquire(size_t bytes, int* idx);
+    void stage_release(int idx);
     int batch_ = 0;           // pairs per lock-step batch on the fused path (0 = choose from the frame size)
     int batch_for(int w, int h) const;
     int run_chunk(Lane& L, int n, const uint8_t* const* d_in0, const uint8_t* const* d_in1, int w, int h, const float* ts, uint8_t* const* d_out, cudaStream_t st);

@@ -358,10 +358,120 @@ __global__ void __launch_bounds__(256, 3) flow_tta_avg_kernel(Flow8 F, int nch, 
             }
     }
 }
+// Same computation, four consecutive elements per thread (fw % 4 == 0 and fh % 4 == 0: every float4 below is aligned and lies
+// entirely inside or outside the blob): row-major blobs are read and written in place as float4 along x, the transposed ones
+// as float4 along y through the shared-memory tile.
+__device__ __forceinline__ void ld4(const float* p, bool rev, float* d) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    if (rev) { d[0] = v.w; d[1] = v.z; d[2] = v.y; d[3] = v.x; }
+    else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+}
+__device__ __forceinline__ void st4(float* p, bool rev, const float* d, float sign) {
+    *reinterpret_cast<float4*>(p) = rev ? make_float4(sign * d[3], sign * d[2], sign * d[1], sign * d[0]) : make_float4(sign * d[0], sign * d[1], sign * d[2], sign * d[3]);
+}
+__global__ void __launch_bounds__(256, 3) flow_tta_avg4_kernel(Flow8 F, int nch, int fw, int fh) {
+    __shared__ float T[4][2][TS][TS + 1];  // transposed orientations 4-7, two channels: T[o - 4][c][x][y]
+    const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+    const int a = threadIdx.x >> 3, b4 = (threadIdx.x & 7) * 4;
+    const size_t plane = (size_t)fw * fh;
+    const int npair = nch >= 4 ? 2 : 1;
+    const int ngroups = npair + (nch == 5 ? 1 : 0);
+    // element offsets of this thread's float4 in the transposed blobs (x = x0 + a slow, y = y0 + b4 .. fast) and in the
+    // row-major ones (y = y0 + a slow, x = x0 + b4 .. fast); reversed axes run backwards in memory
+    const bool tin = x0 + a < fw && y0 + b4 < fh, rin = y0 + a < fh && x0 + b4 < fw;
+    size_t ti[4], ri[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        const bool trf = o == 1 || o == 2, trs = o == 2 || o == 3;  // orientation 4 + o: y (fast) reversed for 5, 6; x (slow) reversed for 6, 7
+        ti[o] = (size_t)(trs ? fw - 1 - (x0 + a) : x0 + a) * fh + (trf ? fh - 4 - (y0 + b4) : y0 + b4);
+        const bool rf = o == 1 || o == 2, rs = o == 2 || o == 3;    // orientation o: x reversed for 1, 2; y reversed for 2, 3
+        ri[o] = (size_t)(rs ? fh - 1 - (y0 + a) : y0 + a) * fw + (rf ? fw - 4 - (x0 + b4) : x0 + b4);
+    }
+#pragma unroll 1
+    for (int g = 0; g < ngroups; g++) {
+        const bool mask = g == npair;
+        const size_t cx = (size_t)(mask ? 4 : 2 * g) * plane, cy = (size_t)(mask ? 4 : 2 * g + 1) * plane;
+        __syncthreads();
+        if (tin) {
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                float v[4];
+                ld4(F.f[4 + o] + cx + ti[o], o == 1 || o == 2, v);
+#pragma unroll
+                for (int j = 0; j < 4; j++) T[o][0][a][b4 + j] = v[j];
+                if (!mask) {
+                    ld4(F.f[4 + o] + cy + ti[o], o == 1 || o == 2, v);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) T[o][1][a][b4 + j] = v[j];
+                }
+            }
+        }
+        __syncthreads();
+        if (rin) {
+            if (mask) {
+                float m[4] = {0.f, 0.f, 0.f, 0.f}, v[4];
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    ld4(F.f[o] + cx + ri[o], o == 1 || o == 2, v);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) m[j] += v[j];
+                }
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) m[j] += T[o][0][b4 + j][a];
+#pragma unroll
+                for (int j = 0; j < 4; j++) m[j] *= 0.125f;
+#pragma unroll
+                for (int o = 0; o < 4; o++) st4(F.f[o] + cx + ri[o], o == 1 || o == 2, m, 1.f);
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) T[o][0][b4 + j][a] = m[j];
+            } else {
+                float fx[4][4], fy[4][4], vx[4], vy[4];
+#pragma unroll
+                for (int o = 0; o < 4; o++) { ld4(F.f[o] + cx + ri[o], o == 1 || o == 2, fx[o]); ld4(F.f[o] + cy + ri[o], o == 1 || o == 2, fy[o]); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // un-rotate and average (signs and the x/y swap of the transposed orientations: SURVEY.md section 2.3)
+                    vx[j] = (fx[0][j] + -fx[1][j] + -fx[2][j] + fx[3][j] + T[0][1][b4 + j][a] + T[1][1][b4 + j][a] + -T[2][1][b4 + j][a] + -T[3][1][b4 + j][a]) * 0.125f;
+                    vy[j] = (fy[0][j] + fy[1][j] + -fy[2][j] + -fy[3][j] + T[0][0][b4 + j][a] + -T[1][0][b4 + j][a] + -T[2][0][b4 + j][a] + T[3][0][b4 + j][a]) * 0.125f;
+                }
+                const float sx[4] = {1.f, -1.f, -1.f, 1.f}, sy[4] = {1.f, 1.f, -1.f, -1.f};
+#pragma unroll
+                for (int o = 0; o < 4; o++) { st4(F.f[o] + cx + ri[o], o == 1 || o == 2, vx, sx[o]); st4(F.f[o] + cy + ri[o], o == 1 || o == 2, vy, sy[o]); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    T[0][0][b4 + j][a] = vy[j];  T[1][0][b4 + j][a] = -vy[j]; T[2][0][b4 + j][a] = -vy[j]; T[3][0][b4 + j][a] = vy[j];
+                    T[0][1][b4 + j][a] = vx[j];  T[1][1][b4 + j][a] = vx[j];  T[2][1][b4 + j][a] = -vx[j]; T[3][1][b4 + j][a] = -vx[j];
+                }
+            }
+        }
+        __syncthreads();
+        if (tin) {
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = T[o][0][a][b4 + j];
+                st4(F.f[4 + o] + cx + ti[o], o == 1 || o == 2, v, 1.f);
+                if (!mask) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = T[o][1][a][b4 + j];
+                    st4(F.f[4 + o] + cy + ti[o], o == 1 || o == 2, v, 1.f);
+                }
+            }
+        }
+    }
+}
 void launch_flow_tta_avg(float* const* f8, int nch, int fw, int fh, cudaStream_t st) {
     Flow8 F;
     for (int i = 0; i < 8; i++) F.f[i] = f8[i];
-    flow_tta_avg_kernel<<<dim3(cdiv(fw, TS), cdiv(fh, TS)), 256, 0, st>>>(F, nch, fw, fh);
+    bool vec = fw % 4 == 0 && fh % 4 == 0;
+    for (int i = 0; i < 8; i++) vec = vec && ((uintptr_t)f8[i] & 15) == 0;
+    if (vec) flow_tta_avg4_kernel<<<dim3(cdiv(fw, TS), cdiv(fh, TS)), 256, 0, st>>>(F, nch, fw, fh);
+    else flow_tta_avg_kernel<<<dim3(cdiv(fw, TS), cdiv(fh, TS)), 256, 0, st>>>(F, nch, fw, fh);
     g_launch_count++;
 }
 
