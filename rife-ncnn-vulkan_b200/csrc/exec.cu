@@ -38,6 +38,7 @@ NetRunner::~NetRunner() {
         cudaFree(w.biasN);
     }
     for (auto& kv : plans_) cudaFree(kv.second->arena);
+    cudaFree(pool_scratch_);
 }
 
 void NetRunner::clear_plans() {
@@ -113,28 +114,30 @@ int NetRunner::init(const Net* net, std::string& err) {
             // Layers wider than one accumulator set run as output-channel slices: convolutions with 256 / 384 / 512 output
             // channels as slices of 128 (the context / fusion pyramids of the 3-net families), deconvolutions with 32 .. 256
             // output channels as slices of 16 (4 parities x 16 = 64 GEMM columns; the deconv epilogue holds a row of them in registers)
-            int nchunks = 1, cchunk = cout;  // output channels per slice
+            int nchunks = 1, cchunk = cout;  // output channels per slice (the last slice may be narrower: zero-padded columns)
             if (isconv && !k5 && N > 192 && N % 128 == 0 && N <= 512) { nchunks = N / 128; cchunk = 128; N = 128; }
-            if (!isconv && !(N == 32 || N == 96) && cout % 16 == 0 && cout >= 32 && cout <= 256) { nchunks = cout / 16; cchunk = 16; ocs = 16; N = 64; }
-            bool nok = isconv ? (N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96 || N == 64);
+            if (!isconv && !(N == 32 || N == 96) && cout % 8 == 0 && cout >= 32 && cout <= 256) { cchunk = 24; nchunks = (cout + 23) / 24; ocs = 24; N = 96; }
+            bool nok = isconv ? (N == 16 || N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192) : (N == 32 || N == 96);
             if (nok && cinp % 16 == 0 && cinp >= 16 && (size_t)cin * cout * kk == L.weight.size()) {
                 std::vector<uint16_t> pk_all;
                 size_t chunk_elems = 0;
                 for (int ch = 0; ch < nchunks; ch++) {
                     std::vector<uint16_t> pk;
                     const float* wc = L.weight.data() + (size_t)ch * cchunk * cin * kk;  // weights are [oc][ic][kk]: a slice of output channels is contiguous
-                    if (k5) pack_conv5x5_weights(wc, cchunk, cin, N, pk);
-                    else if (isconv && s2) pack_conv3x3s2_weights(wc, cchunk, cin, cinp, N, pk);
-                    else if (isconv) pack_conv3x3_weights(wc, cchunk, cin, N, pk);
-                    else pack_deconv4x4_weights(wc, cchunk, cin, ocs, N, pk);
+                    const int cn = std::min(cchunk, cout - ch * cchunk);                // channels of this slice
+                    if (k5) pack_conv5x5_weights(wc, cn, cin, N, pk);
+                    else if (isconv && s2) pack_conv3x3s2_weights(wc, cn, cin, cinp, N, pk);
+                    else if (isconv) pack_conv3x3_weights(wc, cn, cin, N, pk);
+                    else pack_deconv4x4_weights(wc, cn, cin, ocs, N, pk);
                     chunk_elems = pk.size();
                     pk_all.insert(pk_all.end(), pk.begin(), pk.end());
                 }
                 std::vector<float> bN((size_t)N * nchunks, 0.f);
                 if (!L.bias.empty()) {
                     for (int ch = 0; ch < nchunks; ch++) {
-                        if (isconv) for (int i = 0; i < cchunk; i++) bN[(size_t)ch * N + i] = L.bias[ch * cchunk + i];
-                        else for (int p = 0; p < 4; p++) for (int i = 0; i < cchunk; i++) bN[(size_t)ch * N + p * ocs + i] = L.bias[ch * cchunk + i];
+                        const int cn = std::min(cchunk, cout - ch * cchunk);
+                        if (isconv) for (int i = 0; i < cn; i++) bN[(size_t)ch * N + i] = L.bias[ch * cchunk + i];
+                        else for (int p = 0; p < 4; p++) for (int i = 0; i < cn; i++) bN[(size_t)ch * N + p * ocs + i] = L.bias[ch * cchunk + i];
                     }
                 }
                 if (cudaMalloc(&W.wpk, pk_all.size() * 2) != cudaSuccess) { err = "cudaMalloc failed"; return -5; }
@@ -595,7 +598,7 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
             if (W.nchunks > 1) {
                 b.wpk = a.wpk + (size_t)ch * W.chunk_elems;
                 b.bias = a.bias + (size_t)ch * W.tcN;
-                b.Cout = cchunk;
+                b.Cout = std::min(cchunk, L.geti(0, 0) - ch * cchunk);  // the last slice may be narrower
                 if (a.prelu) b.prelu = a.prelu + (size_t)ch * cchunk;
                 if (isconv) {
                     const size_t hw = (size_t)o.h * o.w, cg_stride = a.out_s2d ? hw / 4 : hw;
@@ -709,7 +712,14 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
     } else if (T == "rife.Warp") {
         launch_warp(in(0).p, in(1).p, o.p, in(0).c, in(0).h, in(0).w, st);
     } else if (T == "Pooling") {
-        launch_global_avgpool(in(0).p, o.p, in(0).c, (size_t)in(0).h * in(0).w, st);
+        if (in(0).c > pool_scratch_c_) {
+            cudaFree(pool_scratch_);
+            pool_scratch_ = nullptr;
+            pool_scratch_c_ = 0;
+            if (cudaMalloc(&pool_scratch_, (size_t)global_avgpool_scratch_floats(in(0).c) * sizeof(float)) == cudaSuccess) pool_scratch_c_ = in(0).c;
+            else cudaGetLastError();
+        }
+        launch_global_avgpool(in(0).p, o.p, in(0).c, (size_t)in(0).h * in(0).w, st, pool_scratch_);
     } else if (T == "InnerProduct") {
         const ParamVal* ap = L.get(10);
         launch_innerproduct(in(0).p, W.wT, W.bias, o.p, (int)in(0).count(), o.w, L.geti(9, 0), ap && !ap->af.empty() ? ap->af[0] : 0.f, st);

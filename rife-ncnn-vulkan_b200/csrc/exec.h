@@ -92,6 +92,8 @@ private:
     const std::vector<DeviceWeights>* dwp_ = nullptr;
     bool owns_ = true;
     std::map<std::string, std::unique_ptr<Plan>> plans_;
+    float* pool_scratch_ = nullptr;  // partial sums of the global average pools (per executor: lanes run concurrently)
+    int pool_scratch_c_ = 0;
 };
 
 }  // namespace rife

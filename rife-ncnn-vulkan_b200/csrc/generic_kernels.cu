@@ -244,8 +244,50 @@ __global__ void binary_kernel(const float* __restrict__ a, int ac, size_t ahw, c
         out[i] = v;
     }
 }
+// the two shapes the models use almost exclusively: full x full and full x per-channel scalar (the SE scale): one grid row per
+// channel, no per-element division, float4 when the plane allows
+template <bool BCAST>
+__global__ void binary_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t hw, int op, int vec) {
+    const size_t q = blockIdx.y;
+    const float* pa = a + q * hw;
+    const float* pb = BCAST ? b + q : b + q * hw;
+    float* po = out + q * hw;
+    const float ys = BCAST ? __ldg(pb) : 0.f;
+    auto f = [op](float x, float y) -> float {
+        switch (op) {
+            case B_ADD: return x + y;
+            case B_SUB: return x - y;
+            case B_MUL: return x * y;
+            case B_DIV: return x / y;
+            case B_MAX: return fmaxf(x, y);
+            case B_MIN: return fminf(x, y);
+            case B_RSUB: return y - x;
+            case B_RDIV: return y / x;
+            default: return powf(x, y);
+        }
+    };
+    if (vec) {
+        const size_t n4 = hw / 4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 x = reinterpret_cast<const float4*>(pa)[i];
+            float4 y = make_float4(ys, ys, ys, ys);
+            if (!BCAST) y = reinterpret_cast<const float4*>(pb)[i];
+            reinterpret_cast<float4*>(po)[i] = make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w));
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) po[i] = f(pa[i], BCAST ? ys : pb[i]);
+    }
+}
 void launch_binary(const float* a, int ac, size_t ahw, const float* b, int bc, size_t bhw, float* out, int c, size_t hw, int op, cudaStream_t st) {
     size_t n = (size_t)c * hw;
+    if (ac == c && ahw == hw && bc == c && (bhw == hw || bhw == 1) && hw > 1 && c <= 65535) {
+        const int vec = hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0;
+        const unsigned bx = min(cdiv(vec ? hw / 4 : hw, 256), (unsigned)max(1, (148 * 16) / c));
+        if (bhw == 1) binary_rows_kernel<true><<<dim3(bx, c), 256, 0, st>>>(a, b, out, hw, op, vec);
+        else binary_rows_kernel<false><<<dim3(bx, c), 256, 0, st>>>(a, b, out, hw, op, vec);
+        g_launch_count++;
+        return;
+    }
     binary_kernel<<<min(cdiv(n, 256), 148u * 16), 256, 0, st>>>(a, ac, ahw, b, bc, bhw, out, c, hw, op);
     g_launch_count++;
 }
@@ -316,25 +358,61 @@ void launch_pixelshuffle(const float* in, int c, int h, int w, float* out, int r
     g_launch_count++;
 }
 
-// pooling.cpp:61-105 global average
+// pooling.cpp:61-105 global average.  One block per (channel, slice): kPoolSlices partial sums per channel in a fixed order, then one
+// warp per channel adds the slices (deterministic; a single block per channel left most of the machine idle on big planes).
+constexpr int kPoolSlices = 16;
+__device__ __forceinline__ float block_sum(float s, float* red) {
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    return s;
+}
 __global__ void global_avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, size_t hw) {
     const float* p = in + (size_t)blockIdx.x * hw;
     float s = 0.f;
     for (size_t i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
     __shared__ float red[32];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) out[blockIdx.x] = s / (float)hw;
-    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s / (float)hw;
 }
-void launch_global_avgpool(const float* in, float* out, int c, size_t hw, cudaStream_t st) {
+__global__ void avgpool_partial_kernel(const float* __restrict__ in, float* __restrict__ part, size_t hw) {
+    const size_t per = (hw / 4 + kPoolSlices - 1) / kPoolSlices * 4;  // slice length, a multiple of 4 floats
+    const size_t lo = (size_t)blockIdx.y * per, hi = min(hw, lo + per);
+    const float* p = in + (size_t)blockIdx.x * hw;
+    float s = 0.f;
+    if ((hw & 3) == 0 && (((uintptr_t)in) & 15) == 0) {
+        for (size_t i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) { const float4 v = reinterpret_cast<const float4*>(p)[i]; s += (v.x + v.y) + (v.z + v.w); }
+    } else {
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += p[i];
+    }
+    __shared__ float red[32];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * kPoolSlices + blockIdx.y] = s;
+}
+__global__ void avgpool_final_kernel(const float* __restrict__ part, float* __restrict__ out, int c, size_t hw) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= c) return;
+    float s = 0.f;
+    for (int k = 0; k < kPoolSlices; k++) s += part[(size_t)q * kPoolSlices + k];
+    out[q] = s / (float)hw;
+}
+// scratch: caller-owned room for c * kPoolSlices floats (one per executor, so concurrent lanes do not share it), or null
+void launch_global_avgpool(const float* in, float* out, int c, size_t hw, cudaStream_t st, float* scratch) {
+    if (scratch && hw >= 16384) {
+        avgpool_partial_kernel<<<dim3(c, kPoolSlices), 256, 0, st>>>(in, scratch, hw);
+        avgpool_final_kernel<<<cdiv(c, 128), 128, 0, st>>>(scratch, out, c, hw);
+        g_launch_count += 2;
+        return;
+    }
     global_avgpool_kernel<<<c, 512, 0, st>>>(in, out, hw);
     g_launch_count++;
 }
+int global_avgpool_scratch_floats(int c) { return c * kPoolSlices; }
 
 // innerproduct.cpp: out[p] = act(bias[p] + sum_i w[p][i]*x[i]) ; one warp per output
 __global__ void innerproduct_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,

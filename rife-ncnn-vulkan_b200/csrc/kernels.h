@@ -43,7 +43,8 @@ void launch_eltwise_sum2(const float* a, const float* b, float c0, float c1, flo
 void launch_interp_bilinear(const float* in, int c, int h, int w, float* out, int oh, int ow, cudaStream_t st);
 void launch_pixelshuffle(const float* in, int c, int h, int w, float* out, int r, cudaStream_t st);
 void launch_warp(const float* img, const float* flow, float* out, int c, int h, int w, cudaStream_t st);
-void launch_global_avgpool(const float* in, float* out, int c, size_t hw, cudaStream_t st);
+void launch_global_avgpool(const float* in, float* out, int c, size_t hw, cudaStream_t st, float* scratch = nullptr);
+int global_avgpool_scratch_floats(int c);
 void launch_innerproduct(const float* in, const float* w, const float* bias, float* out, int nin, int nout, int act, float p0, cudaStream_t st);
 
 // ---- RIFE stages, hbm_kernels.cu ----

@@ -838,7 +838,7 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     return 0;
 }
 
-int tc_conv_tile_rows(int N) { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }
+int tc_conv_tile_rows(int N) { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }  // 2 * MT
 
 template <int N, int MT, int STAGES>
 static int launch_n(const TcConvArgs& a, const CUtensorMap& tm, cudaStream_t st) {
@@ -894,6 +894,7 @@ int launch_tc_conv(TcConvArgs a, const void* in, cudaStream_t st) {
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -5;
     switch (a.N) {
+        case 16: return launch_n<16, 4, 4>(a, tm, st);
         case 32: return launch_n<32, 4, 4>(a, tm, st);
         case 48: return launch_n<48, 4, 3>(a, tm, st);
         case 64: return launch_n<64, 4, 3>(a, tm, st);

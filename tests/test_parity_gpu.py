@@ -496,10 +496,13 @@ def test_null_frame_in_a_batch_is_rejected_before_anything_is_queued(pkg):
 
 @pytest.mark.parametrize("model", ["rife-v4.6", "rife-v4"])
 @pytest.mark.parametrize("case", ["synth", "large_motion", "readme_images"])
-def test_packed_head_tensors_stay_within_one_lsb(pkg, model, case):
-    """Option "head_pack": the block-head tensors as ONE fp16 plane whose slots 12..15 carry the lo parts of the four flow
-    channels (fused_v46_kernels.cuh: 32 instead of 64 bytes per pixel, half the tensor work in the first stride-2 conv).
-    Same +-1 LSB / 50 dB bar against the oracle as the default."""
+def test_packed_head_tensors_are_an_opt_in_approximation(pkg, model, case):
+    """Option "head_pack" (default OFF): the block-head tensors as ONE fp16 plane whose slots 12..15 carry the lo parts of the
+    four flow channels (fused_v46_kernels.cuh: 32 instead of 64 bytes per pixel, half the tensor work in the first stride-2
+    conv, +6.7 % fps).  Measured in round 2 (profiles/r2_s2): the synthetic rife-v4.6 pairs stay within 1 LSB, but the README
+    frames reach 7 LSB on 0.03 % of the values and rife-v4 2-3 LSB -- the warped frames / mask need their lo parts too -- so it
+    does NOT meet the +-1 LSB bar and is not the default.  This test pins what the option does deliver (PSNR > 60 dB, fewer
+    than 0.1 % of the values off by 2 or more) and that the default, on the same pair, stays within 1 LSB."""
     _need(model)
     if case == "synth":
         a, b = parity.synth.pair(640, 360)
@@ -513,10 +516,9 @@ def test_packed_head_tensors_stay_within_one_lsb(pkg, model, case):
             b = np.array(Image.open(os.path.join(d, "1.png")).convert("RGB"))
         except Exception:
             pytest.skip("README frames or PIL not available")
-    opts = {"head_pack": 1}
-    if a.shape[1] % 32:
-        opts["cpu_crop_quirk"] = 1
+    base = {"cpu_crop_quirk": 1} if a.shape[1] % 32 else {}
     ref, _ = parity.run_oracle(model, a, b, 0.5)
-    out = parity.run_gpu(pkg, model, a, b, 0.5, options=opts)
-    res = parity.compare(out, ref)
-    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["share_ne"] < 0.02, res
+    res = parity.compare(parity.run_gpu(pkg, model, a, b, 0.5, options=dict(base, head_pack=1)), ref)
+    assert res["max_abs_diff"] <= 8 and res["psnr_db"] > 60 and res["share_ge2"] < 1e-3, res
+    res0 = parity.compare(parity.run_gpu(pkg, model, a, b, 0.5, options=base), ref)
+    assert res0["max_abs_diff"] <= 1 and res0["psnr_db"] > 50, res0
