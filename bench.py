@@ -461,7 +461,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa(local)  # pinned host buffers next to the GPU: the e2e legs are bound by the host link
+    numa = bind_to_gpu_numa(local)
+    gpu_cpus = os.sched_getaffinity(0)  # pinned host buffers next to the GPU: the e2e legs are bound by the host link
 
     import torch
     import __graft_entry__ as g
@@ -525,6 +526,7 @@ def main():
                         rc = 3
                 except Exception as e:  # the oracle binary did not travel / wrong ISA: report, do not fake
                     r["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+            os.sched_setaffinity(0, gpu_cpus)  # back next to the GPU for the remaining host-buffer legs
             if world == 1 and not args.no_process_leg and plain_v46:
                 r["e2e_process"] = e2e_process_block(ctx, wl, args)
         results[wl] = r

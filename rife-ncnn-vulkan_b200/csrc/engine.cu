@@ -644,10 +644,11 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             if (r) { rc = r; break; }
             cudaEventRecord(ev_comp_[s], L.st);
             for (int u = 0; u < nfe; u++) { cudaEventRecord(fe[u]->read_done, L.st); fe[u]->reading = true; }
-            cudaStreamWaitEvent(st_copy_[1], ev_comp_[s], 0);
-            for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, st_copy_[1]);
+            cudaStream_t sd = st_copy_[1 + (chunk & 1)];
+            cudaStreamWaitEvent(sd, ev_comp_[s], 0);
+            for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, sd);
             g_d2h_bytes += (unsigned long long)cn * nb;
-            cudaEventRecord(ev_d2h_[s], st_copy_[1]);
+            cudaEventRecord(ev_d2h_[s], sd);
             used[s] = 1;
             cn = 0;
             chunk++;
@@ -657,8 +658,7 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     // reuse or free its buffers
     cudaError_t e = cudaStreamSynchronize(st_copy_[0]);
     for (Lane* L : lanes_) { cudaError_t e2 = cudaStreamSynchronize(L->st); if (e2 != cudaSuccess) e = e2; }
-    cudaError_t e3 = cudaStreamSynchronize(st_copy_[1]);
-    if (e3 != cudaSuccess) e = e3;
+    for (int k = 1; k < 3; k++) { cudaError_t e3 = cudaStreamSynchronize(st_copy_[k]); if (e3 != cudaSuccess) e = e3; }
     for (auto& f : frames_) { f.reading = false; if (!frame_cache_ || rc) f.host = nullptr; }
     if (rc) { cudaGetLastError(); return rc; }
     if (e != cudaSuccess) { set_error(std::string("CUDA failure: ") + cudaGetErrorString(e)); return -2; }

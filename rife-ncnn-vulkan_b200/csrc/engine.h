@@ -104,7 +104,7 @@ private:
     std::vector<Lane*> lanes_;
     int nlanes_ = 2;
     std::string packed_;    // serialized model (param text + bin bytes per net)
-    cudaStream_t st_copy_[2] = {nullptr, nullptr};
+    cudaStream_t st_copy_[3] = {nullptr, nullptr, nullptr};  // [0] H2D, [1] / [2] D2H (chunks alternate: two copies in flight keep the link busier than one engine's queue)
     static const int kSlots = 8;
     cudaEvent_t ev_h2d_[kSlots] = {}, ev_comp_[kSlots] = {}, ev_d2h_[kSlots] = {}, ev_entry_ = nullptr;
     mutable std::mutex mu_;
