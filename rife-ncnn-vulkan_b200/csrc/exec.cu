@@ -108,7 +108,8 @@ int NetRunner::init(const Net* net, std::string& err) {
             int N = 0, ocs = 0, s2 = 0, cinp = cin, k5 = 0;
             // 5x5 s1 p2 (the residual blocks of the rife / HD / UHD / anime flownets): one kernel row per pipeline stage
             if (is5 && L.geti(3, 1) == 1 && L.geti(4, 0) == 2 && L.geti(2, 1) == 1 && (cout == 48 || cout == 96 || cout == 128 || cout == 192)) { N = cout; k5 = 1; }
-            if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout;
+            // (8-channel heads: padded to 16 GEMM columns; the C8 storage of a blob is allocated in multiples of 16 channels)
+            if (isconv && k == 3 && L.geti(3, 1) == 1 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) N = cout == 8 ? 16 : cout;
             if (isconv && k == 3 && L.geti(3, 1) == 2 && L.geti(4, 0) == 1 && L.geti(2, 1) == 1) { N = cout; s2 = 1; if (cin < 16) cinp = 16; }
             if (!isconv) { ocs = (cout + 7) / 8 * 8; N = 4 * ocs; }
             // Layers wider than one accumulator set run as output-channel slices: convolutions with 256 / 384 / 512 output
@@ -564,12 +565,12 @@ int NetRunner::exec_step(Plan& plan, const Step& s, cudaStream_t st, std::string
         if (isconv) {
             a.epi = TC_EPI_C8;
             a.out = c8ptr(s.out_blob);
-            a.out_plane = o.count();
+            a.out_plane = (size_t)((o.c + 15) / 16 * 16) * o.h * o.w;  // C8 storage is allocated and converted in multiples of 16 channels
             a.out_s2d = plan.c8_s2d[plan.root[s.out_blob]];
             a.split_out = plan.split;
             if (s.fused_add_blob >= 0) {
                 a.res = c8ptr(s.fused_add_blob);
-                a.res_plane = plan.blobs[s.fused_add_blob].count();
+                a.res_plane = (size_t)((plan.blobs[s.fused_add_blob].c + 15) / 16 * 16) * o.h * o.w;
                 a.res_split = plan.split;
                 a.res_mode = 1;
             }
