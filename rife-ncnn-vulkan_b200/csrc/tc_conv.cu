@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     // a.wres: the packed weights of the whole layer stay in shared memory for the life of the (persistent) CTA and a
     // pipeline stage carries activations only; otherwise every stage re-streams its 16-channel weight slice from L2
     // (per tile that is more bytes than the activations themselves).
-    const int stage_bytes = ((A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)) + 1023) & ~1023;
+    // a.ks > 1 (resident weights only): a pipeline stage carries ks consecutive 16-channel chunks (sub-slabs), i.e. one barrier
+    // round trip (full / empty) per ks chunks instead of per chunk
+    const int sub_bytes = ((A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)) + 1023) & ~1023;
+    const int KS = a.ks > 1 ? a.ks : 1;
+    const int stage_bytes = sub_bytes * KS;
     const int NST = a.stages;  // pipeline depth (<= 8), chosen by the launcher
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_bytes + 1024);  // +1024: overrun pad for the last tap of the last slab
     uint64_t* empty = full + 8;
@@ -310,17 +314,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
                 const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
                 const int x0 = tx * TVALID, y0 = ty * (RPA * MT);
-                for (int kc = 0; kc < KC; kc++, it++) {
-                    mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = smem + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_PLANE * nplanes + (a.wres ? 0 : W_BYTES)));
+                for (int kc = 0, q = 0; kc < KC; kc++, it++) {
+                    if (q == 0) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(KS * (A_PLANE * nplanes + (a.wres ? 0 : W_BYTES))));
+                    }
+                    uint8_t* st = smem + (size_t)s * stage_bytes + (size_t)q * sub_bytes;
                     for (int p = 0; p < nplanes; p++) {
                         if constexpr (TAPS == 5) tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 2) * 4, y0 - 2 + kc % 5, p * (2 * KCP) + 2 * (kc / 5), bimg);
                         else tma_load_4d(st + p * A_PLANE, &tmA, &full[s], (x0 - 1) * (WIDE ? 2 : 4), y0 - 1, p * (2 * KC) + 2 * kc, bimg);  // 16 B per pixel = 4 u32 / 2 u64 elements
                     }
                     if (!a.wres) bulk_load_1d(st + nplanes * A_PLANE, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, &full[s]);
                     if (dbg && it - dskip < 12u) dbg[1 + it - dskip] = clock64();
-                    if (++s == NST) { s = 0; ph ^= 1; }
+                    if (++q == KS) { q = 0; if (++s == NST) { s = 0; ph ^= 1; } }
                 }
             }
         }
@@ -354,11 +360,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
 #pragma unroll
                     for (int m = 0; m < MT; m++) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);
                 }
-                for (int kc = 0; kc < KC; kc++, it++) {
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
+                for (int kc = 0, q = 0; kc < KC; kc++, it++) {
+                    if (q == 0) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                    }
                     if (dbg && it - dskip < 12u && lane == 0) dbg[16 + it - dskip] = clock64();
-                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes + (size_t)q * sub_bytes);
                     const uint32_t a_base = (st >> 4) | A_LBO;
                     const uint32_t b_base = ((a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE) >> 4) | B_LBO;
                     constexpr int ROWSTEP16 = (RPA * TWP * 16) >> 4;  // accumulator m+1 starts RPA tile rows further
@@ -459,9 +467,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                             }
                     }
                     if (a.dbg_flags & 64) umma_commit_elect(scratch_bar);  // timing experiment: what does one more commit per stage cost?
-                    umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
+                    if (q == KS - 1) umma_commit_elect(&empty[s]);  // frees the stage once the MMAs above have read it
                     if (dbg && it - dskip < 12u && lane == 0) dbg[32 + it - dskip] = clock64();
-                    if (++s == NST) { s = 0; ph ^= 1; }
+                    if (++q == KS) { q = 0; if (++s == NST) { s = 0; ph ^= 1; } }
                 }
                 umma_commit_elect(&acc_full[buf]);
             }
@@ -807,14 +815,18 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     const size_t stage_a = (size_t)((A_PLANE * nplanes + 1023) & ~1023), stage_aw = (size_t)((A_PLANE * nplanes + W_BYTES + 1023) & ~1023);
     // resident weights need at least STAGES activation-only stages next to the whole layer
     a.wres = wres_ok && TAPS == 9 && ((STAGES * stage_a + consts + ident_bytes + 127) & ~(size_t)127) + w_all <= budget;
-    const int stage_bytes = (int)(a.wres ? stage_a : stage_aw);
+    // chunks per pipeline stage (RIFE_B200_KS, default TC_KS_DEFAULT): resident-weight kernels only, KC divisible, >= 2 stages left
+    static const int ks_env = getenv("RIFE_B200_KS") ? atoi(getenv("RIFE_B200_KS")) : TC_KS_DEFAULT;
     const size_t fixed = a.wres ? consts + ident_bytes + 127 + w_all : consts + (a.res_mode == 3 ? ident_bytes : 0);
+    a.ks = 1;
+    if (a.wres && ks_env > 1 && (a.Cin / 16) % ks_env == 0 && (budget - fixed) / (stage_a * ks_env) >= 2) a.ks = ks_env;
+    const int stage_bytes = (int)(a.wres ? stage_a * a.ks : stage_aw);
     // pipeline depth: what shared memory allows (the stages are what hides the L2 / HBM latency of the activation tiles)
     static const int max_stages = getenv("RIFE_B200_STAGES") ? atoi(getenv("RIFE_B200_STAGES")) : 8;
     int nst = (int)((budget - fixed) / stage_bytes);
     if (nst > max_stages) nst = max_stages;
     if (nst > 8) nst = 8;
-    if (nst < STAGES) nst = STAGES;
+    if (nst < STAGES && a.ks == 1) nst = STAGES;
     a.stages = nst;
     const size_t smem = a.wres ? (((size_t)nst * stage_bytes + consts + ident_bytes + 127) & ~(size_t)127) + w_all : (size_t)nst * stage_bytes + fixed;
     if (smem > 227 * 1024) return -2;

@@ -35,6 +35,7 @@ struct TcConvArgs {
     int out_cgroups;        // 8-channel groups of the output TENSOR (0 = Cout / 8); larger when this launch writes a channel slice of it
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
+    int ks;                         // filled by the launcher: 16-channel chunks per pipeline stage (resident-weight kernels; RIFE_B200_KS)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
     int wide;                       // filled by the launcher: one-row accumulators / 126-column tiles (tc_wide_enabled)
     int pair;                       // filled by the launcher: bit 0 paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled), bit 1 narrow identity tap
@@ -51,6 +52,7 @@ int tc_conv_tile_rows(int N);
 constexpr int TC_PAIR_DEFAULT = 3;
 int tc_pair_mode();
 bool tc_pair_enabled(int N);
+constexpr int TC_KS_DEFAULT = 1;
 constexpr int TC_WIDE_DEFAULT = 0;  // measured slower than the paired 2-row form (profiles/README.md, round 2 session 2): 739 vs 687 us per 8 launches
 bool tc_wide_enabled(int N);
 
