@@ -200,6 +200,28 @@ class Ctx:
     pass
 
 
+def host_link_gbs():
+    """Measured rate of this GPU's host link with pinned memory (256 MiB copies, CUDA events, best of 3 per direction): the bound
+    of the e2e legs, which move 6.2 MB (1080p) / 24.9 MB (4K) of result per frame device -> host."""
+    import torch
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        out[name] = round(n / (best * 1e-3) / 1e9, 1)
+    return out
+
+
 def measure(ctx, workload, args, headline):
     """All GPU-side measurements of one resolution.  Returns a dict (rank-local; times are already max-reduced over ranks)."""
     import torch
@@ -508,6 +530,7 @@ def main():
     ctx.pkg, ctx.eng, ctx.dist, ctx.world, ctx.rank, ctx.local = pkg, eng, dist, world, rank, local
     ctx.l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     ctx.stream = torch.cuda.Stream()
+    link = host_link_gbs() if rank == 0 else None
 
     order = [args.workload] + ([] if args.only else [k for k in WORKLOADS if k != args.workload])
     results, rc = {}, 0
@@ -556,7 +579,7 @@ def main():
                            "images_per_lockstep_batch": head["kb"], "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "recompute_fm": eng.get_option("recompute_fm"), "head_pack": eng.get_option("head_pack"),
                            "wide_tiles": int(os.environ.get("RIFE_B200_WIDE", "1")),
                            "fused_path": head["fast"], "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic",
-                           "host_numa": numa},
+                           "host_numa": numa, "host_link_GBps": link},
                 "gflop_per_frame": hb["gflop_per_frame"], "model_tflops": hb["value"] * GFLOP_PER_FRAME[args.workload] / 1000.0 if plain_v46 else None,
                 "e2e": hb["e2e"], "e2e_process": hb["e2e_process"], "gpu_launches": hb["gpu_launches"], "clocks": hb["clocks"], "roofline": hb["roofline"],
                 "stages_us_per_lockstep_batch": hb["stages_us_per_lockstep_batch"], "parity": hb["parity"], "cpu_baseline": hb["cpu_baseline"], "out_checksum": hb["out_checksum"],

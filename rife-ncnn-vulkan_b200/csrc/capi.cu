@@ -465,6 +465,8 @@ extern "C" int rife_b200_bench_conv_batched(int gpuid, void* cuda_stream, int ci
     a.dbg = g_dbg_dev;
     a.dbg_skip = g_dbg_skip;
     a.dbg_flags = g_dbg_flags;
+    // knock-out timing without the in-kernel timeline (tools/knockout.py): RIFE_B200_DBG_FLAGS is read on every call
+    if (!g_dbg_dev) if (const char* e = getenv("RIFE_B200_DBG_FLAGS")) a.dbg_flags = atoi(e);
     if (batch > 1) {
         // reinterpret the tall synthetic tensor as `batch` images: per image [planes][C/8][h/batch][w][8]; the values are
         // arbitrary, only the addressing pattern matters for timing

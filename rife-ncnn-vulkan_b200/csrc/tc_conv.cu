@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     const uint32_t o_lo = (smem_u32(ones) >> 4) | (((uint32_t)(128 * 16) >> 4) << 16);
                     const uint32_t bb_lo = (smem_u32(biasB) >> 4) | B_LBO;
 #pragma unroll
-                    for (int m = 0; m < MT; m++) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);
+                    for (int m = 0; m < MT; m++)
+                        if (!(a.dbg_flags & 2) || tcount < 2) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);  // (flag 2: timing experiment, bias MMAs only on the first use of each buffer)
                 }
                 for (int kc = 0, q = 0; kc < KC; kc++, it++) {
                     if (q == 0) {
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 const uint32_t b_addr = a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE;
 #pragma unroll
                                 for (int dx = 0; dx < 3; dx++) {
+                                    if ((a.dbg_flags & 4) && dx > 0) continue;  // timing experiment: a third of the taps (results wrong)
                                     const uint32_t b_lo = ((b_addr + (uint32_t)(dx * (2 * 3 * N * 16))) >> 4) | B3_LBO;
                                     const uint32_t a_lo = a_base + (uint32_t)dx;
                                     if (nplanes == 2) {
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                             }
                         }
-                        if (a.res_mode == 3 && (a.pair & 2)) {
+                        if (a.res_mode == 3 && (a.pair & 2) && !(a.dbg_flags & 1)) {  // (flag 1: timing experiment without the identity tap)
                             constexpr uint32_t I16_LBO = ((uint32_t)(16 * 16) >> 4) << 16;
                             constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                             const uint32_t b_lo = (smem_u32(ident) >> 4) | I16_LBO;
