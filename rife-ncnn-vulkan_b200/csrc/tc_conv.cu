@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
     const int KCP = a.Cin / 16;                    // K chunks per parity sub-image (all of them for stride 1)
     const int KC = TAPS == 9 ? KCP : (TAPS == 5 ? 5 * KCP : 4 * KCP);
     const uint32_t dskip = (uint32_t)(a.dbg_skip * KC);  // diagnostics: first recorded pipeline iteration
+    const int krot = a.krot ? (int)((blockIdx.x * 5u) % (unsigned)KC) : 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -311,10 +312,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                 for (int kc = 0; kc < KC; kc++) bulk_load_1d(wres + (size_t)kc * W_BYTES, a.wpk + (size_t)kc * (W_BYTES / 2), W_BYTES, wbar);
             }
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
+                // a.rev: this launch walks the tiles in reverse raster order.  Consecutive layers of a chain alternate, so a layer
+                // starts with the part of its input the previous layer wrote last -- the part still in the 126 MB L2
+                const int teff = a.rev ? ntiles - 1 - tile : tile;
+                const int bimg = teff / tiles_img, trem = teff - bimg * tiles_img;
                 const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
                 const int x0 = tx * TVALID, y0 = ty * (RPA * MT);
-                for (int kc = 0, q = 0; kc < KC; kc++, it++) {
+                for (int kk = 0, q = 0; kk < KC; kk++, it++) {
+                    // a.krot (streamed weights): every CTA starts its K loop at a different chunk, so the CTAs of a wave do not all
+                    // ask L2 for the same weight lines at the same moment (accumulation order is free: the bias MMA comes first)
+                    const int kc = kk + krot < KC ? kk + krot : kk + krot - KC;
+                    if (a.dbg_flags & 16) {  // timing experiment: no loads at all (the MMAs read whatever the slabs hold)
+                        if (q == 0) mbar_wait(&empty[s], ph ^ 1);
+                        if (q == KS - 1) mbar_arrive(&full[s]);
+                        if (++q == KS) { q = 0; if (++s == NST) { s = 0; ph ^= 1; } }
+                        continue;
+                    }
                     if (q == 0) {
                         mbar_wait(&empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&full[s], (uint32_t)(KS * (A_PLANE * nplanes + (a.wres ? 0 : W_BYTES))));
@@ -361,7 +374,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     for (int m = 0; m < MT; m++)
                         if (!(a.dbg_flags & 2) || tcount < 2) umma_f16_elect(acc0 + m * N, o_lo, DESC_HI, bb_lo, DESC_HI, idesc, 0u);  // (flag 2: timing experiment, bias MMAs only on the first use of each buffer)
                 }
-                for (int kc = 0, q = 0; kc < KC; kc++, it++) {
+                for (int kk = 0, q = 0; kk < KC; kk++, it++) {
+                    const int kc = kk + krot < KC ? kk + krot : kk + krot - KC;  // same rotation as the producer
                     if (q == 0) {
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
@@ -492,7 +506,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int buf = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
-            const int bimg = tile / tiles_img, trem = tile - bimg * tiles_img;
+            const int teff = a.rev ? ntiles - 1 - tile : tile;
+            const int bimg = teff / tiles_img, trem = teff - bimg * tiles_img;
             const int tx = trem % a.tiles_x, ty = trem / a.tiles_x;
             const int x0 = tx * TVALID, y0 = ty * (RPA * MT);
             const int x = x0 + xr;
@@ -820,6 +835,8 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     // chunks per pipeline stage (RIFE_B200_KS, default TC_KS_DEFAULT): resident-weight kernels only, KC divisible, >= 2 stages left
     static const int ks_env = getenv("RIFE_B200_KS") ? atoi(getenv("RIFE_B200_KS")) : TC_KS_DEFAULT;
     const size_t fixed = a.wres ? consts + ident_bytes + 127 + w_all : consts + (a.res_mode == 3 ? ident_bytes : 0);
+    static const int krot_env = getenv("RIFE_B200_KROT") ? atoi(getenv("RIFE_B200_KROT")) : TC_KROT_DEFAULT;
+    a.krot = (!a.wres && krot_env) ? 1 : 0;
     a.ks = 1;
     if (a.wres && ks_env > 1 && (a.Cin / 16) % ks_env == 0 && (budget - fixed) / (stage_a * ks_env) >= 2) a.ks = ks_env;
     const int stage_bytes = (int)(a.wres ? stage_a * a.ks : stage_aw);

@@ -35,13 +35,15 @@ struct TcConvArgs {
     int out_cgroups;        // 8-channel groups of the output TENSOR (0 = Cout / 8); larger when this launch writes a channel slice of it
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
+    int rev;                        // walk the tiles in reverse raster order (alternated by the caller across the layers of a chain: L2 reuse)
+    int krot;                       // filled by the launcher: per-CTA rotation of the K loop (streamed-weight kernels; RIFE_B200_KROT)
     int ks;                         // filled by the launcher: 16-channel chunks per pipeline stage (resident-weight kernels; RIFE_B200_KS)
     int wres;                       // filled by the launcher: the layer's packed weights stay resident in shared memory
     int wide;                       // filled by the launcher: one-row accumulators / 126-column tiles (tc_wide_enabled)
     int pair;                       // filled by the launcher: bit 0 paired MMA issue over [dy2 | dy0 | dy1] weight blocks (tc_pair_enabled), bit 1 narrow identity tap
     unsigned long long* dbg;        // optional timeline buffer: 64 clock64 slots per CTA (diagnostics)
     int dbg_skip;                   // tiles (per CTA) to skip before the timeline starts recording
-    int dbg_flags;                  // timing experiments only (results wrong): 1 = no identity tap, 2 = no bias MMAs after the first tiles, 4 = a third of the taps, 8 = empty epilogue, 64 = one extra tcgen05.commit per stage
+    int dbg_flags;                  // timing experiments only (results wrong): 1 = no identity tap, 2 = no bias MMAs after the first tiles, 4 = a third of the taps, 8 = empty epilogue, 16 = no activation / weight loads, 64 = one extra tcgen05.commit per stage
 };
 
 // `in`: C8 planar activation [planes][Cin/8][H][W][8] fp16.  Returns 0 on success.
@@ -52,6 +54,7 @@ int tc_conv_tile_rows(int N);
 constexpr int TC_PAIR_DEFAULT = 3;
 int tc_pair_mode();
 bool tc_pair_enabled(int N);
+constexpr int TC_KROT_DEFAULT = 0;
 constexpr int TC_KS_DEFAULT = 2;  // measured (profiles/r2_s6): chain of IFBlock 3 704 -> 692 us, IFBlock 2 414 -> 403 us per 8 launches
 constexpr int TC_WIDE_DEFAULT = 0;  // measured slower than the paired 2-row form (profiles/README.md, round 2 session 2): 739 vs 687 us per 8 launches
 bool tc_wide_enabled(int N);
