@@ -417,7 +417,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                     } else if constexpr (TAPS == 9) {
                         bool paired = false;
                         if constexpr (2 * N <= 256) paired = (a.pair & 1) != 0;
-                        if (paired) {
+                        bool chunk_block = false;
+                        if constexpr (2 * N <= 256 && (N <= 64 || N == 96 || N == 128) && (N % 16 == 0) && !(N > 64 && MT != 2) && !(N <= 64 && MT != 4)) {
+                            // the shipped path: every MMA of the chunk in ONE asm block with literal operand offsets (tools/gen_mma_issue.py
+                            // chunk_block); the per-tap blocks below remain for the diagnostic knock-outs and the unpaired layout
+                            chunk_block = paired && a.dbg_flags == 0 && a.chunk_issue && (a.res_mode != 3 || (a.pair & 2));
+                            if (chunk_block) {
+                                constexpr uint32_t B3_LBO = ((uint32_t)(3 * N * 16) >> 4) << 16;
+                                constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                constexpr uint32_t I16_LBO = ((uint32_t)(16 * 16) >> 4) << 16;
+                                constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                const uint32_t b_addr = a.wres ? wres_addr + (uint32_t)(kc * W_BYTES) : st + nplanes * A_PLANE;
+                                const uint32_t b_lo = (b_addr >> 4) | B3_LBO;
+                                const uint32_t id_lo = (smem_u32(ident) >> 4) | I16_LBO;
+                                const uint32_t id_on = a.res_mode == 3 ? 1u : 0u;
+                                if (nplanes == 2) umma_issue_chunk_paired<N, MT, 2>(acc0, a_base, b_lo, DESC_HI, idesc, idesc2, id_on, id_lo, idesc16, acc0 + (uint32_t)(16 * kc));
+                                else umma_issue_chunk_paired<N, MT, 1>(acc0, a_base, b_lo, DESC_HI, idesc, idesc2, id_on, id_lo, idesc16, acc0 + (uint32_t)(16 * kc));
+                            }
+                        }
+                        if (chunk_block) {
+                        } else if (paired) {
                             // Paired issue: the view of halo rows 2j, 2j+1 is the dy=0 operand of accumulator j AND the dy=2
                             // operand of accumulator j-1, whose TMEM columns are adjacent -- one 2N-column MMA against
                             // [W_dy2 | W_dy0] replaces two N-column ones (A is fetched from shared memory once instead of
@@ -451,7 +470,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_conv3x3_kernel(const __grid_co
                                 else umma_issue_tap<MT, 1, (A_PLANE >> 4), ROWSTEP16, N>(acc0, a_lo, b_lo, DESC_HI, idesc, 1u);
                             }
                         }
-                        if (a.res_mode == 3 && (a.pair & 2) && !(a.dbg_flags & 1)) {  // (flag 1: timing experiment without the identity tap)
+                        if (chunk_block) {
+                        } else if (a.res_mode == 3 && (a.pair & 2) && !(a.dbg_flags & 1)) {  // (flag 1: timing experiment without the identity tap)
                             constexpr uint32_t I16_LBO = ((uint32_t)(16 * 16) >> 4) << 16;
                             constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                             const uint32_t b_lo = (smem_u32(ident) >> 4) | I16_LBO;
@@ -835,6 +855,8 @@ static int launch_t(const TcConvArgs& a_in, const CUtensorMap& tm, cudaStream_t 
     // chunks per pipeline stage (RIFE_B200_KS, default TC_KS_DEFAULT): resident-weight kernels only, KC divisible, >= 2 stages left
     static const int ks_env = getenv("RIFE_B200_KS") ? atoi(getenv("RIFE_B200_KS")) : TC_KS_DEFAULT;
     const size_t fixed = a.wres ? consts + ident_bytes + 127 + w_all : consts + (a.res_mode == 3 ? ident_bytes : 0);
+    static const int chunk_env = getenv("RIFE_B200_CHUNK_ISSUE") ? atoi(getenv("RIFE_B200_CHUNK_ISSUE")) : TC_CHUNK_ISSUE_DEFAULT;
+    a.chunk_issue = chunk_env;
     static const int krot_env = getenv("RIFE_B200_KROT") ? atoi(getenv("RIFE_B200_KROT")) : TC_KROT_DEFAULT;
     a.krot = (!a.wres && krot_env) ? 1 : 0;
     a.ks = 1;

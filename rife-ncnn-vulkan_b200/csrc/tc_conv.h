@@ -35,6 +35,7 @@ struct TcConvArgs {
     int out_cgroups;        // 8-channel groups of the output TENSOR (0 = Cout / 8); larger when this launch writes a channel slice of it
     int tiles_x, tiles_y, num_sms;  // filled by the launcher
     int stages;                     // filled by the launcher: pipeline depth (<= 8)
+    int chunk_issue;                // filled by the launcher: all MMAs of a 16-channel chunk from one asm block (RIFE_B200_CHUNK_ISSUE)
     int rev;                        // walk the tiles in reverse raster order (alternated by the caller across the layers of a chain: L2 reuse)
     int krot;                       // filled by the launcher: per-CTA rotation of the K loop (streamed-weight kernels; RIFE_B200_KROT)
     int ks;                         // filled by the launcher: 16-channel chunks per pipeline stage (resident-weight kernels; RIFE_B200_KS)
@@ -54,6 +55,7 @@ int tc_conv_tile_rows(int N);
 constexpr int TC_PAIR_DEFAULT = 3;
 int tc_pair_mode();
 bool tc_pair_enabled(int N);
+constexpr int TC_CHUNK_ISSUE_DEFAULT = 1;
 constexpr int TC_KROT_DEFAULT = 0;
 constexpr int TC_KS_DEFAULT = 2;  // measured (profiles/r2_s6): chain of IFBlock 3 704 -> 692 us, IFBlock 2 414 -> 403 us per 8 launches
 constexpr int TC_WIDE_DEFAULT = 0;  // measured slower than the paired 2-row form (profiles/README.md, round 2 session 2): 739 vs 687 us per 8 launches

@@ -87,6 +87,42 @@ def wide_block(mt, np_):
             % (body, ", ".join(ops)))
 
 
+def chunk_block(n, mt, np_):
+    """ALL MMAs of one 16-channel chunk of a paired-layout 3x3 stride-1 conv in ONE asm block (27 + MT taps x NP planes): per kernel
+    column dx the paired rows, then the dy = 1 taps, finally the narrow identity tap (predicated on %6).  Same order as the per-tap
+    blocks it replaces (bit-identical accumulation); every operand offset is a literal, so between two MMAs there is nothing
+    but three uniform adds -- the per-block preamble (elect, register -> uniform-register moves, divergence checks: ~40 SASS
+    instructions) is paid once per chunk instead of seven times."""
+    twp, rowstep = 64, 128
+    aplane = 2 * (2 * mt + 2) * twp  # 16-byte units
+    L = ['"{\\n"', '".reg .pred q, pi, qi, pt;\\n"', '"setp.eq.b32 pt, 0, 0;\\n"', '".reg .b64 da, db;\\n"', '".reg .b32 al, tm, bl;\\n"', '"elect.sync _|q, 0xffffffff;\\n"',
+         '"setp.ne.b32 pi, %6, 0;\\n"', '"and.pred qi, q, pi;\\n"']
+
+    def mma(a_off, b_reg, b_off, t_reg, t_off, idc, pred="q"):
+        return ['"add.u32 al, %%1, %d;\\n"' % a_off, '"add.u32 bl, %s, %d;\\n"' % (b_reg, b_off), '"add.u32 tm, %s, %d;\\n"' % (t_reg, t_off),
+                '"mov.b64 da, {al, %3};\\n"', '"mov.b64 db, {bl, %3};\\n"', '"@%s tcgen05.mma.cta_group::1.kind::f16 [tm], da, db, %s, pt;\\n"' % (pred, idc)]
+    for dx in range(3):
+        bblk = dx * 2 * 3 * n
+        for j in range(mt + 1):
+            for pl in range(np_):
+                a_off = dx + j * rowstep + pl * aplane
+                if j == 0:
+                    L += mma(a_off, "%2", bblk + n, "%0", 0, "%4")
+                elif j == mt:
+                    L += mma(a_off, "%2", bblk, "%0", (mt - 1) * n, "%4")
+                else:
+                    L += mma(a_off, "%2", bblk, "%0", (j - 1) * n, "%5")
+        for m in range(mt):
+            for pl in range(np_):
+                L += mma(dx + twp + m * rowstep + pl * aplane, "%2", bblk + 2 * n, "%0", m * n, "%4")
+    for m in range(mt):
+        for pl in range(np_):
+            L += mma(twp + 1 + m * rowstep + pl * aplane, "%7", 0, "%9", m * n, "%8", pred="qi")
+    L.append('"}\\n"')
+    body = "\n            ".join(L)
+    return ("        asm volatile(\n            %s\n            ::\"r\"(acc), \"r\"(a_lo), \"r\"(b_lo), \"r\"(desc_hi), \"r\"(idesc), \"r\"(idesc2), \"r\"(ident_on), \"r\"(ident_b_lo), \"r\"(idesc16), \"r\"(acc_ident));\n" % body)
+
+
 def main():
     o = ["// Generated by tools/gen_mma_issue.py -- do not edit.  One asm block per filter tap issues all MT x NP MMAs of that tap;",
          "// descriptor / TMEM address arithmetic stays inside the block so ptxas keeps it on the uniform datapath.",
@@ -124,6 +160,19 @@ def main():
         for np_ in (1, 2):
             o.append("    %sif constexpr (MT == %d && NP == %d) {" % ("" if first else "else ", mt, np_))
             o.append(wide_block(mt, np_).rstrip("\n"))
+            o.append("    }")
+            first = False
+    o.append("}")
+    o += ["// Whole-chunk issue (see tools/gen_mma_issue.py chunk_block): every MMA of one 16-channel chunk of a paired 3x3 stride-1 conv in one",
+          "// asm block with literal operand offsets.  a_lo = slab address >> 4 | LBO, b_lo = address of the chunk's [dx][half][3N] weight blocks >> 4 | LBO(3N rows).",
+          "template <int N, int MT, int NP>",
+          "__device__ __forceinline__ void umma_issue_chunk_paired(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t idesc2, uint32_t ident_on,",
+          "                                                        uint32_t ident_b_lo, uint32_t idesc16, uint32_t acc_ident) {"]
+    first = True
+    for n, mt in ((16, 4), (32, 4), (48, 4), (64, 4), (96, 2), (128, 2)):
+        for np_ in (1, 2):
+            o.append("    %sif constexpr (N == %d && MT == %d && NP == %d) {" % ("" if first else "else ", n, mt, np_))
+            o.append(chunk_block(n, mt, np_).rstrip("\n"))
             o.append("    }")
             first = False
     o.append("}")
