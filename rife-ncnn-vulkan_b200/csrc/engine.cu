@@ -31,6 +31,7 @@ Engine::Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v
     // process-wide default of option "recompute_fm" (lets a whole test run exercise one setting)
     if (const char* e = getenv("RIFE_B200_RECOMPUTE_FM")) { int v = atoi(e); recompute_fm_ = v < 0 ? 0 : (v > 2 ? 2 : v); }
     if (const char* e = getenv("RIFE_B200_COMBINE")) combine_ = atoi(e) != 0;
+    if (tta_) nlanes_ = 4;  // the 8 orientations of a pair are dealt to the lanes (tta_fork / tta_join)
 }
 
 void Lane::release() {
@@ -45,6 +46,8 @@ void Lane::release() {
     for (auto& a : flowr) for (auto& b : a) b.release();
     for (auto& b : outp) b.release();
     if (done) cudaEventDestroy(done);
+    if (fork) cudaEventDestroy(fork);
+    fork = nullptr;
     if (st) cudaStreamDestroy(st);
     done = nullptr;
     st = nullptr;
@@ -90,6 +93,7 @@ int Engine::make_lanes(int n) {
         Lane* L = new Lane();
         if (cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking) != cudaSuccess) { delete L; set_error("stream creation failed"); return -2; }
         cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&L->fork, cudaEventDisableTiming);
         if (!lanes_.empty())
             for (int i = 0; i < 3; i++)
                 if (lanes_[0]->run[i]) { L->run[i] = new NetRunner(); L->run[i]->share_from(*lanes_[0]->run[i]); }
@@ -504,7 +508,7 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
     std::lock_guard<std::mutex> lk(mu_);
     if (!loaded_) { set_error("process before load"); return -4; }
     cudaSetDevice(gpuid_);
-    const int nl = (int)lanes_.size();
+    const int nl = tta_ ? 1 : (int)lanes_.size();  // spatial TTA: lane 0 coordinates, the other lanes are its helpers (tta_fork / tta_join)
     const int B = batch_for(w, h);
     if (use_user_stream_) {
         cudaEventRecord(ev_entry_, user_stream_);
@@ -586,7 +590,7 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     std::lock_guard<std::mutex> lk(mu_);
     if (!loaded_) { set_error("process before load"); return -4; }
     cudaSetDevice(gpuid_);
-    const int nl = (int)lanes_.size();
+    const int nl = tta_ ? 1 : (int)lanes_.size();  // spatial TTA: lane 0 coordinates, the other lanes are its helpers
     const int nslots = 2 * nl <= kSlots ? 2 * nl : kSlots;
     const int B = batch_for(w, h);
     int per = B;
@@ -683,6 +687,21 @@ int Engine::run_device(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int 
 
 typedef std::vector<std::pair<std::string, Tensor>> Inputs;
 
+// TTA modes: the 8 orientations (x 2 time directions) of one pair are independent graph walks between the flow-averaging
+// points (rife.cpp:1541-1949, 3432-3823).  The lane that serves the pair (the coordinator) deals them round-robin to ALL lanes
+// of the engine -- each with its own stream, plans and arena -- so the many small kernels of different orientations overlap;
+// fork() / join() order the helpers' streams after / before the coordinator's.  (process_batch gives TTA pairs to lane 0 only.)
+void Engine::tta_fork(Lane& L) {
+    if (!tta_) return;
+    cudaEventRecord(L.fork, L.st);
+    for (Lane* H : lanes_) if (H != &L) cudaStreamWaitEvent(H->st, L.fork, 0);
+}
+void Engine::tta_join(Lane& L) {
+    if (!tta_) return;
+    for (Lane* H : lanes_) if (H != &L) { cudaEventRecord(H->done, H->st); cudaStreamWaitEvent(L.st, H->done, 0); }
+}
+Lane& Engine::tta_lane(Lane& L, int job) { return tta_ ? *lanes_[(size_t)job % lanes_.size()] : L; }
+
 // ---- rife-v4 / v4.6: rife.cpp:3204-4401 -------------------------------------------------------------------
 int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st) {
     const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;  // rife.cpp:3229-3230
@@ -723,22 +742,26 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
 
     Tensor fl[4][8], flr[4][8];
     for (int fi = 0; fi < 4; fi++) {
+        tta_fork(L);
         for (int ti = 0; ti < nti; ti++) {
+            Lane& H = tta_lane(L, ti);
+            NetRunner& FH = *H.run[0];
             {   // rife.cpp:3432-3451 / 4233-4252: inject the already merged flow0..fi-1, extract flow<fi>
                 Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], fl[k][ti]});
-                if (F.run(in, {kFlow[fi]}, o, st, err)) { set_error(err); return -5; }
-                fl[fi][ti] = keep(o[0], L.flow[fi][ti], st);
+                if (FH.run(in, {kFlow[fi]}, o, H.st, err)) { set_error(err); return -5; }
+                fl[fi][ti] = keep(o[0], L.flow[fi][ti], H.st);
             }
             if (ttat_) {
                 Inputs in = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
                 for (int k = 0; k < fi; k++) in.push_back({kFlow[k], flr[k][ti]});
-                if (F.run(in, {kFlow[fi]}, o, st, err)) { set_error(err); return -5; }
-                flr[fi][ti] = keep(o[0], L.flowr[fi][ti], st);
+                if (FH.run(in, {kFlow[fi]}, o, H.st, err)) { set_error(err); return -5; }
+                flr[fi][ti] = keep(o[0], L.flowr[fi][ti], H.st);
                 // rife.cpp:3476-3512 / 4277-4312
-                launch_temporal_merge_v2(fl[fi][ti].p, flr[fi][ti].p, (size_t)fl[fi][ti].h * fl[fi][ti].w, 1, st);
+                launch_temporal_merge_v2(fl[fi][ti].p, flr[fi][ti].p, (size_t)fl[fi][ti].h * fl[fi][ti].w, 1, H.st);
             }
         }
+        tta_join(L);
         if (tta_) {  // rife.cpp:3515-3668 (+ reversed set :3670-3823)
             float* f8[8];
             for (int ti = 0; ti < 8; ti++) f8[ti] = fl[fi][ti].p;
@@ -750,18 +773,22 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
         }
     }
     const float* ins[16];
+    tta_fork(L);
     for (int ti = 0; ti < nti; ti++) {
+        Lane& H = tta_lane(L, ti);
+        NetRunner& FH = *H.run[0];
         Inputs in = {{"in0", I0[ti]}, {"in1", I1[ti]}, {"in2", T[ti / 4]}};
         for (int k = 0; k < 4; k++) in.push_back({kFlow[k], fl[k][ti]});
-        if (F.run(in, {"out0"}, o, st, err)) { set_error(err); return -5; }
-        ins[ti] = keep(o[0], L.outp[ti], st).p;
+        if (FH.run(in, {"out0"}, o, H.st, err)) { set_error(err); return -5; }
+        ins[ti] = keep(o[0], L.outp[ti], H.st).p;
         if (ttat_) {
             Inputs inr = {{"in0", I1[ti]}, {"in1", I0[ti]}, {"in2", TR[ti / 4]}};
             for (int k = 0; k < 4; k++) inr.push_back({kFlow[k], flr[k][ti]});
-            if (F.run(inr, {"out0"}, o, st, err)) { set_error(err); return -5; }
-            ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
+            if (FH.run(inr, {"out0"}, o, H.st, err)) { set_error(err); return -5; }
+            ins[nti + ti] = keep(o[0], L.outp[8 + ti], H.st).p;
         }
     }
+    tta_join(L);
     if (tta_) launch_postproc(ins, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, bgr_, st);  // rife.cpp:4060-4144
     else launch_postproc(ins, 2, wp, hp, d_out, w, h, cpu_crop_quirk_, bgr_, st);       // rife.cpp:4356-4371
     return 0;
@@ -771,9 +798,6 @@ int Engine::run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, i
 int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st) {
     const int wp = (w + 31) / 32 * 32, hp = (h + 31) / 32 * 32;
     const size_t plane = (size_t)wp * hp;
-    NetRunner& F = *L.run[0];
-    NetRunner& C = *L.run[1];
-    NetRunner& U = *L.run[2];
     std::string err;
     std::vector<Tensor> o;
     const int nti = tta_ ? 8 : 1;
@@ -786,44 +810,49 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
         I0[ti] = Tensor::chw(L.pad0.f() + (size_t)ti * 3 * plane, 3, th, tw);
         I1[ti] = Tensor::chw(L.pad1.f() + (size_t)ti * 3 * plane, 3, th, tw);
     }
-    // flownet(a, b) -> flow at half resolution; uhd: rife.cpp:2212-2229
-    auto flownet = [&](const Tensor& a, const Tensor& b, DevBuf& dst, Tensor& flow) -> int {
+    // flownet(a, b) -> flow at half resolution, on lane H (its executor, stream and scratch); uhd: rife.cpp:2212-2229
+    auto flownet = [&](Lane& H, const Tensor& a, const Tensor& b, DevBuf& dst, Tensor& flow) -> int {
+        NetRunner& FH = *H.run[0];
+        cudaStream_t sh = H.st;
         if (uhd_) {
             Tensor ad = Tensor::chw(nullptr, 3, (int)(a.h * 0.5f), (int)(a.w * 0.5f)), bd = ad;
-            L.tmp[0].ensure(ad.count() * 4);
-            L.tmp[1].ensure(ad.count() * 4);
-            ad.p = L.tmp[0].f();
-            bd.p = L.tmp[1].f();
-            launch_interp_bilinear(a.p, 3, a.h, a.w, ad.p, ad.h, ad.w, st);
-            launch_interp_bilinear(b.p, 3, b.h, b.w, bd.p, bd.h, bd.w, st);
+            H.tmp[0].ensure(ad.count() * 4);
+            H.tmp[1].ensure(ad.count() * 4);
+            ad.p = H.tmp[0].f();
+            bd.p = H.tmp[1].f();
+            launch_interp_bilinear(a.p, 3, a.h, a.w, ad.p, ad.h, ad.w, sh);
+            launch_interp_bilinear(b.p, 3, b.h, b.w, bd.p, bd.h, bd.w, sh);
             Inputs in = {{"input0", ad}, {"input1", bd}};
-            if (F.run(in, {"flow"}, o, st, err)) { set_error(err); return -5; }
+            if (FH.run(in, {"flow"}, o, sh, err)) { set_error(err); return -5; }
             Tensor fd = o[0];
             flow = Tensor::chw(nullptr, fd.c, (int)(fd.h * 2.f), (int)(fd.w * 2.f));
             dst.ensure(flow.count() * 4);
             flow.p = dst.f();
-            launch_interp_bilinear(fd.p, fd.c, fd.h, fd.w, flow.p, flow.h, flow.w, st);
-            launch_unary(flow.p, flow.p, flow.count(), U_MUL_S, 2.f, 0.f, st);
+            launch_interp_bilinear(fd.p, fd.c, fd.h, fd.w, flow.p, flow.h, flow.w, sh);
+            launch_unary(flow.p, flow.p, flow.count(), U_MUL_S, 2.f, 0.f, sh);
         } else {
             Inputs in = {{"input0", a}, {"input1", b}};
-            if (F.run(in, {"flow"}, o, st, err)) { set_error(err); return -5; }
-            flow = keep(o[0], dst, st);
+            if (FH.run(in, {"flow"}, o, sh, err)) { set_error(err); return -5; }
+            flow = keep(o[0], dst, sh);
         }
         return 0;
     };
     Tensor fl[8], flr[8];
-    for (int ti = 0; ti < nti; ti++)
-        if (flownet(I0[ti], I1[ti], L.flow[0][ti], fl[ti])) return -5;
-    auto merge = [&](int ti) {
+    auto merge = [&](int ti, cudaStream_t sm) {
         size_t n = (size_t)fl[ti].h * fl[ti].w;
-        if (v2_) launch_temporal_merge_v2(fl[ti].p, flr[ti].p, n, 0, st);  // rife.cpp:2285-2306
-        else launch_temporal_merge_v1(fl[ti].p, flr[ti].p, n, st);         // rife.cpp:2307-2319
+        if (v2_) launch_temporal_merge_v2(fl[ti].p, flr[ti].p, n, 0, sm);  // rife.cpp:2285-2306
+        else launch_temporal_merge_v1(fl[ti].p, flr[ti].p, n, sm);         // rife.cpp:2307-2319
     };
-    if (ttat_)
-        for (int ti = 0; ti < nti; ti++) {
-            if (flownet(I1[ti], I0[ti], L.flowr[0][ti], flr[ti])) return -5;
-            merge(ti);
+    tta_fork(L);
+    for (int ti = 0; ti < nti; ti++) {
+        Lane& H = tta_lane(L, ti);
+        if (flownet(H, I0[ti], I1[ti], L.flow[0][ti], fl[ti])) return -5;
+        if (ttat_) {
+            if (flownet(H, I1[ti], I0[ti], L.flowr[0][ti], flr[ti])) return -5;
+            merge(ti, H.st);
         }
+    }
+    tta_join(L);
     if (tta_) {  // rife.cpp:1541-1719, reversed :1721-1896, second merge :1898-1949
         float* f8[8];
         for (int ti = 0; ti < 8; ti++) f8[ti] = fl[ti].p;
@@ -831,12 +860,17 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
         if (ttat_) {
             for (int ti = 0; ti < 8; ti++) f8[ti] = flr[ti].p;
             launch_flow_tta_avg(f8, v2_ ? 4 : 2, fl[0].w, fl[0].h, st);
-            for (int ti = 0; ti < 8; ti++) merge(ti);
+            for (int ti = 0; ti < 8; ti++) merge(ti, st);
         }
     }
     static const char* kCtx[4] = {"f1", "f2", "f3", "f4"};
     const float* ins[16];
+    tta_fork(L);
     for (int ti = 0; ti < nti; ti++) {
+        Lane& H = tta_lane(L, ti);
+        NetRunner& CH = *H.run[1];
+        NetRunner& UH = *H.run[2];
+        cudaStream_t sh = H.st;
         Tensor c0[4], c1[4];
         Tensor f0 = fl[ti], f1 = fl[ti];
         if (v2_) {  // Slice 4 -> 2 + 2, rife.cpp:2322-2330
@@ -846,27 +880,28 @@ int Engine::run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w,
         }
         {   // rife.cpp:2335-2351
             Inputs in = {{"input.1", I0[ti]}, {"flow.0", f0}};
-            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { set_error(err); return -5; }
-            for (int k = 0; k < 4; k++) c0[k] = keep(o[k], L.ctx[0][k], st);
+            if (CH.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, sh, err)) { set_error(err); return -5; }
+            for (int k = 0; k < 4; k++) c0[k] = keep(o[k], H.ctx[0][k], sh);
         }
         {   // rife.cpp:2352-2368
             Inputs in = {{"input.1", I1[ti]}, {v2_ ? "flow.0" : "flow.1", f1}};
-            if (C.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, st, err)) { set_error(err); return -5; }
-            for (int k = 0; k < 4; k++) c1[k] = keep(o[k], L.ctx[1][k], st);
+            if (CH.run(in, {kCtx[0], kCtx[1], kCtx[2], kCtx[3]}, o, sh, err)) { set_error(err); return -5; }
+            for (int k = 0; k < 4; k++) c1[k] = keep(o[k], H.ctx[1][k], sh);
         }
         {   // rife.cpp:2372-2388
             Inputs in = {{"img0", I0[ti]}, {"img1", I1[ti]}, {"flow", fl[ti]}, {"3", c0[0]}, {"4", c0[1]}, {"5", c0[2]}, {"6", c0[3]},
                          {"7", c1[0]}, {"8", c1[1]}, {"9", c1[2]}, {"10", c1[3]}};
-            if (U.run(in, {"output"}, o, st, err)) { set_error(err); return -5; }
-            ins[ti] = (tta_ || ttat_) ? keep(o[0], L.outp[ti], st).p : o[0].p;
-            }
+            if (UH.run(in, {"output"}, o, sh, err)) { set_error(err); return -5; }
+            ins[ti] = (tta_ || ttat_) ? keep(o[0], L.outp[ti], sh).p : o[0].p;
+        }
         if (ttat_) {  // rife.cpp:2391-2409
             Inputs in = {{"img0", I1[ti]}, {"img1", I0[ti]}, {"flow", flr[ti]}, {"3", c1[0]}, {"4", c1[1]}, {"5", c1[2]}, {"6", c1[3]},
                          {"7", c0[0]}, {"8", c0[1]}, {"9", c0[2]}, {"10", c0[3]}};
-            if (U.run(in, {"output"}, o, st, err)) { set_error(err); return -5; }
-            ins[nti + ti] = keep(o[0], L.outp[8 + ti], st).p;
+            if (UH.run(in, {"output"}, o, sh, err)) { set_error(err); return -5; }
+            ins[nti + ti] = keep(o[0], L.outp[8 + ti], sh).p;
         }
     }
+    tta_join(L);
     if (tta_) launch_postproc(ins, ttat_ ? 16 : 8, wp, hp, d_out, w, h, 0, bgr_, st);
     else launch_postproc(ins, ttat_ ? 2 : 1, wp, hp, d_out, w, h, cpu_crop_quirk_, bgr_, st);
     return 0;

@@ -30,6 +30,7 @@ struct DevBuf {
 struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t fork = nullptr;  // spatial TTA: the coordinator's fork point for its helper lanes
     NetRunner* run[3] = {nullptr, nullptr, nullptr};
     V46Runner* fast = nullptr;  // hand-scheduled rife-v4 / v4.6 path (plain mode, precision tier 1)
     DevBuf pad0, pad1;          // the 8 orientations of the two padded frames, planar fp32 (generic path)
@@ -76,6 +77,9 @@ private:
     int run_v4(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, float t, uint8_t* d_out, cudaStream_t st);
     int run_v1v2(Lane& L, const uint8_t* d_in0, const uint8_t* d_in1, int w, int h, uint8_t* d_out, cudaStream_t st);
     int make_lanes(int n);
+    void tta_fork(Lane& L);
+    void tta_join(Lane& L);
+    Lane& tta_lane(Lane& L, int job);
     void setup_fast();      // (re)creates the per-lane fast runners and validates them against the generic executor
     Tensor keep(const Tensor& t, DevBuf& b, cudaStream_t st);  // copy a plan-owned tensor into an engine buffer
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu_); last_error_ = s; }

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--frames", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--lanes", type=int, default=0, help="0 = library default (2; 4 for spatial-TTA engines, whose orientations are dealt to the lanes)")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as g
@@ -32,6 +33,8 @@ def main():
     eng = pkg.RIFE(0, args.tta, args.tta_temporal, args.uhd, 1, v2, v4)
     eng.load(parity.model_dir(args.model))
     eng.set_option("precision", args.precision)
+    if args.lanes > 0:
+        eng.set_option("lanes", args.lanes)
     a, b = parity.synth.pair(args.w, args.h)
     da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     out = torch.empty_like(da)
@@ -44,8 +47,8 @@ def main():
         eng.process_ptr(da.data_ptr(), db.data_ptr(), args.w, args.h, 0.5, out.data_ptr(), device=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print("%s %dx%d tta=%d tta_temporal=%d precision=%d: %.3f frames/s (%.1f ms/frame, %d launches/frame)" %
-          (args.model, args.w, args.h, args.tta, args.tta_temporal, args.precision, args.frames / dt, 1000 * dt / args.frames, (pkg.launch_count() - l0) // args.frames))
+    print("%s %dx%d tta=%d tta_temporal=%d precision=%d lanes=%d: %.3f frames/s (%.1f ms/frame, %d launches/frame)" %
+          (args.model, args.w, args.h, args.tta, args.tta_temporal, args.precision, eng.get_option("lanes"), args.frames / dt, 1000 * dt / args.frames, (pkg.launch_count() - l0) // args.frames))
 
 
 if __name__ == "__main__":
