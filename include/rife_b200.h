@@ -72,7 +72,7 @@ int rife_b200_process_batch_device(rife_b200_t* handle, int n, const unsigned ch
 
 /* precision tier: 0 = exact (fp32 CUDA-core path for every layer), 1 = fast (tcgen05 fp16 tensor-core
  * convolutions with split-precision operands where needed).  Default 1 when the model supports it. */
-/* other keys: "lanes" (1-4 concurrent streams), "batch" (pairs per lock-step batch on the fused path, 0 = auto),
+/* other keys: "lanes" (1-8 concurrent streams; default 2, 8 for spatial-TTA engines, whose 8 orientations are dealt to the lanes), "batch" (pairs per lock-step batch on the fused path, 0 = auto),
  * "plain_blocks" (bit k: IFBlock k's residual chain uses plain fp16 activations instead of split hi+lo; default 12),
  * "fast" (0/1 fused rife-v4.6 path), "async" (0/1), "fuse" (0/1 epilogue fusion in the fp32 path),
  * "combine" (0/1, default 1: concurrent rife_b200_process calls on one handle run as one lock-step batch),

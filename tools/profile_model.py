@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--frames", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--lanes", type=int, default=0, help="0 = library default (2; 4 for spatial-TTA engines, whose orientations are dealt to the lanes)")
+    ap.add_argument("--lanes", type=int, default=0, help="0 = library default (2; 8 for spatial-TTA engines, whose orientations are dealt to the lanes)")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as g
