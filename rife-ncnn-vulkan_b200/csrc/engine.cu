@@ -31,6 +31,7 @@ Engine::Engine(int gpuid, bool tta, bool tta_temporal, bool uhd, bool v2, bool v
     // process-wide default of option "recompute_fm" (lets a whole test run exercise one setting)
     if (const char* e = getenv("RIFE_B200_RECOMPUTE_FM")) { int v = atoi(e); recompute_fm_ = v < 0 ? 0 : (v > 2 ? 2 : v); }
     if (const char* e = getenv("RIFE_B200_COMBINE")) combine_ = atoi(e) != 0;
+    if (const char* e = getenv("RIFE_B200_D2H")) d2h_on_lane_ = atoi(e) != 0;
     if (tta_) nlanes_ = 8;  // the 8 orientations of a pair are dealt to the lanes (tta_fork / tta_join): measured 7.1 (1 lane) / 13.8 (4) / 14.7 (8) fps for rife-anime 1080p -x -z
 }
 
@@ -648,8 +649,12 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             if (r) { rc = r; break; }
             cudaEventRecord(ev_comp_[s], L.st);
             for (int u = 0; u < nfe; u++) { cudaEventRecord(fe[u]->read_done, L.st); fe[u]->reading = true; }
-            cudaStream_t sd = st_copy_[1 + (chunk & 1)];
-            cudaStreamWaitEvent(sd, ev_comp_[s], 0);
+            // results go home either on the lane's own stream (the copy sits between this lane's chunks while the other lanes keep the
+            // GPU busy; no cross-stream hand-over on the critical path) or on two dedicated copy streams (RIFE_B200_D2H=0, and always
+            // with a single lane, where the first form would serialise copy and compute)
+            const bool on_lane = d2h_on_lane_ && nl > 1;
+            cudaStream_t sd = on_lane ? L.st : st_copy_[1 + (chunk & 1)];
+            if (!on_lane) cudaStreamWaitEvent(sd, ev_comp_[s], 0);
             for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, sd);
             g_d2h_bytes += (unsigned long long)cn * nb;
             cudaEventRecord(ev_d2h_[s], sd);
