@@ -1,21 +1,16 @@
 #!/bin/bash
-# Round 2, GPU session 13: the shipped state -- smoke(), full suite, the default bench line, config 4 / 5 side measurements.
-O=gpurun_out/r2_s13
+# Round 2, GPU session 14: where the results' device -> host copies are queued (RIFE_B200_D2H) -- e2e A/B at 1080p and 4K.
+O=gpurun_out/r2_s14
 mkdir -p $O
 T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a $O/summary.txt; }
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
-stamp "smoke(): rc=$? $(tail -1 $O/smoke.log)"
-timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider --maxfail=30 > $O/pytest_gpu.log 2>&1
-stamp "pytest -m gpu: rc=$? $(tail -1 $O/pytest_gpu.log)"
-timeout 600 python bench.py > $O/bench.json 2> $O/bench.err
-stamp "bench.py rc=$? $(cut -c1-200 $O/bench.json)"
-timeout 120 python tools/profile_model.py --model rife-anime --tta --tta-temporal --frames 3 > $O/anime_tta_fps.txt 2>&1
-stamp "$(tail -1 $O/anime_tta_fps.txt)"
-timeout 300 python bench.py --only --no-cpu-baseline --no-process-leg --model rife-v4 --timestep 0.25 > $O/bench_v4.json 2> $O/bench_v4.err
-stamp "bench rife-v4 rc=$? $(cut -c1-120 $O/bench_v4.json)"
-RIFE_BENCH_PAIRS=8 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled --csv --log-file $O/launches_1080p.csv \
-    python bench.py --only --no-cpu-baseline --no-process-leg --steps 2 --warmup 3 --lanes 1 > $O/ncu_launches.log 2>&1
-python tools/summarise_launches.py $O/launches_1080p.csv 30 > $O/launches_1080p_summary.txt 2>&1
-stamp "ncu launch list of the bench command done"
+B="python bench.py --only --no-cpu-baseline --no-process-leg"
+show() { python -c "import json,sys; d=json.load(open(sys.argv[1])); print('value %.0f e2e %.0f link %s numa %s' % (d['value'], d['e2e']['value'], d['config'].get('host_link_GBps'), d['config'].get('host_numa')))" $1; }
+for i in 1 2 3; do
+  RIFE_B200_D2H=0 timeout 300 $B > $O/bench_d2h0_$i.json 2> $O/bench_d2h0_$i.err; stamp "D2H=0 #$i $(show $O/bench_d2h0_$i.json)"
+  RIFE_B200_D2H=1 timeout 300 $B > $O/bench_d2h1_$i.json 2> $O/bench_d2h1_$i.err; stamp "D2H=1 #$i $(show $O/bench_d2h1_$i.json)"
+done
+RIFE_B200_D2H=0 timeout 300 $B --workload 4k > $O/bench4k_d2h0.json 2> $O/bench4k_d2h0.err; stamp "4K D2H=0 $(show $O/bench4k_d2h0.json)"
+RIFE_B200_D2H=1 timeout 300 $B --workload 4k > $O/bench4k_d2h1.json 2> $O/bench4k_d2h1.err; stamp "4K D2H=1 $(show $O/bench4k_d2h1.json)"
+RIFE_B200_D2H=1 timeout 300 $B --lanes 3 > $O/bench_d2h1_l3.json 2> $O/bench_d2h1_l3.err; stamp "D2H=1 lanes 3 $(show $O/bench_d2h1_l3.json)"
 cat $O/summary.txt
