@@ -93,7 +93,7 @@ def bind_to_gpu_numa(local):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML in-process, every 5 ms;
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML in-process, every 100 ms;
     falls back to nvidia-smi when pynvml is unavailable)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -111,6 +111,11 @@ class ClockSampler(threading.Thread):
             self.nvml = None
 
     def run(self):
+        # 100 ms: polling NVML every 5 ms stalled this process's own cudaMemcpyAsync calls by 10-250 ms now and then (the e2e leg
+        # dropped from ~2150 to 1000-1800 frames/s, profiles/r2_s17_sampler_stall.txt); 0 = no sampling (diagnosis only)
+        period = float(os.environ.get("RIFE_BENCH_SAMPLER_MS", "100")) / 1000.0
+        if period <= 0:
+            return
         while not self.stop_flag:
             try:
                 if self.nvml:
@@ -122,7 +127,7 @@ class ClockSampler(threading.Thread):
                     for bit, name in self.REASONS.items():
                         if r & bit:
                             self.reasons.add(name)
-                    time.sleep(0.005)
+                    time.sleep(period)
                 else:
                     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
                     o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
@@ -307,14 +312,17 @@ def measure(ctx, workload, args, headline):
     barrier()
     cb0 = pkg.copy_bytes()
     t0 = time.perf_counter()
+    each = []
     for _ in range(args.steps):
-        step_host()
+        t1 = time.perf_counter()
+        step_host()  # returns when the step's results are in the host buffers
+        each.append(round(1000.0 * (time.perf_counter() - t1), 2))
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
     cb1 = pkg.copy_bytes()
     res["clocks"] = sampler.summary()
     res["e2e"] = {"value": total_pairs * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int((cb1[0] - cb0[0]) // args.steps),
-                  "d2h_bytes_per_step": int((cb1[1] - cb0[1]) // args.steps),
+                  "d2h_bytes_per_step": int((cb1[1] - cb0[1]) // args.steps), "ms_each_step_this_rank": each,
                   "note": "bytes counted by the library on this rank; a frame shared by several pairs of a call is uploaded once"}
     res["out_checksum"] = int(out_host[0].to(torch.int64).sum().item()) if pairs else 0
 

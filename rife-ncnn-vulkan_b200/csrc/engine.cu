@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "kernels.h"
 
@@ -560,15 +561,20 @@ int Engine::process_batch_device(int n, const uint8_t* const* d_in0, const uint8
 Engine::FrameEntry* Engine::frame_lookup(const uint8_t* host, size_t nb, FrameEntry* const* cur, int ncur, bool* hit) {
     const size_t kMaxFrames = 4 * (size_t)V46_MAX_BATCH * 2 + 2;  // ~4 chunks of 8 pairs with all-distinct frames
     if (frames_.capacity() < kMaxFrames) frames_.reserve(kMaxFrames);  // entries are referenced by pointer: never reallocate
+    // order of preference on a miss: an entry nobody owns (a call that re-sends few frames keeps using the same few buffers), a
+    // new entry, the least recently used one outside the current chunk
     FrameEntry* lru = nullptr;
+    FrameEntry* spare = nullptr;
     for (auto& f : frames_) {
         if (f.host == host && f.nb == nb) { *hit = true; f.stamp = ++frame_clock_; return &f; }
+        if (!f.host) { if (!spare) spare = &f; continue; }
         bool in_cur = false;
         for (int u = 0; u < ncur; u++) in_cur = in_cur || cur[u] == &f;
         if (!in_cur && (!lru || f.stamp < lru->stamp)) lru = &f;
     }
     *hit = false;
-    if (frames_.size() < kMaxFrames) {
+    if (spare) lru = spare;
+    else if (frames_.size() < kMaxFrames) {
         frames_.emplace_back();
         lru = &frames_.back();
         if (cudaEventCreateWithFlags(&lru->read_done, cudaEventDisableTiming) != cudaSuccess) { frames_.pop_back(); return nullptr; }
@@ -578,6 +584,17 @@ Engine::FrameEntry* Engine::frame_lookup(const uint8_t* host, size_t nb, FrameEn
     lru->nb = nb;
     lru->stamp = ++frame_clock_;
     return lru;
+}
+
+// A larger frame size than the table's buffers were made for: drop the small buffers in one go.  (Growing them one by one as
+// the LRU order reaches them puts a device-wide cudaFree into the pipeline of the next several calls.)
+void Engine::frames_fit(size_t nb) {
+    bool small = false;
+    for (auto& f : frames_) small = small || (f.buf.cap && f.buf.cap < nb);
+    if (!small) return;
+    sync_all();
+    for (auto& f : frames_)
+        if (f.buf.cap && f.buf.cap < nb) { f.buf.release(); f.host = nullptr; f.reading = false; }
 }
 
 // Host frames, pipelined by chunk: H2D runs on one copy stream, compute on lane chunk mod lanes, D2H on the other copy
@@ -598,6 +615,7 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     if (n < per * nl) per = (n + nl - 1) / nl;
     if (per < 1) per = 1;
     if (out_u8_.size() < (size_t)kSlots * V46_MAX_BATCH) out_u8_.resize((size_t)kSlots * V46_MAX_BATCH);
+    frames_fit(nb);
     std::vector<int> used(nslots, 0);
     const uint8_t* c0[V46_MAX_BATCH];
     const uint8_t* c1[V46_MAX_BATCH];
@@ -608,6 +626,14 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     int nfe = 0;
     int cn = 0, chunk = 0;
     int rc = 0;
+    // RIFE_B200_TRACE_BATCH=1: per chunk, CUDA-event times of compute start / end and of the end of its D2H copies (stderr)
+    static const bool trace = getenv("RIFE_B200_TRACE_BATCH") && atoi(getenv("RIFE_B200_TRACE_BATCH")) != 0;
+    struct Tr { cudaEvent_t a, b, c; int lane; };
+    std::vector<Tr> tr;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    std::vector<double> host_issue;
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double tr_first[4] = {0, 0, 0, 0};  // chunk 0: host time after the uploads are queued / the waits / the kernels / the downloads
     for (int i = 0; i <= n && !rc; i++) {
         if (i < n) {
             if (ts[i] == 0.f || ts[i] == 1.f) {
@@ -642,11 +668,16 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
         if (cn == per || (i == n && cn > 0)) {
             const int s = chunk % nslots;
             Lane& L = *lanes_[chunk % nl];
+            if (trace && chunk == 0) tr_first[0] = host_ms();
             cudaEventRecord(ev_h2d_[s], st_copy_[0]);
             cudaStreamWaitEvent(L.st, ev_h2d_[s], 0);
             if (used[s]) cudaStreamWaitEvent(L.st, ev_d2h_[s], 0);  // output buffers of slot s have been downloaded
+            if (trace) { Tr t; cudaEventCreate(&t.a); cudaEventCreate(&t.b); cudaEventCreate(&t.c); t.lane = chunk % nl; cudaEventRecord(t.a, L.st); tr.push_back(t); }
+            if (trace && chunk == 0) tr_first[1] = host_ms();
             int r = run_chunk(L, cn, c0, c1, w, h, ct, co, L.st);
             if (r) { rc = r; break; }
+            if (trace && chunk == 0) tr_first[2] = host_ms();
+            if (trace) cudaEventRecord(tr.back().b, L.st);
             cudaEventRecord(ev_comp_[s], L.st);
             for (int u = 0; u < nfe; u++) { cudaEventRecord(fe[u]->read_done, L.st); fe[u]->reading = true; }
             // results go home either on the lane's own stream (the copy sits between this lane's chunks while the other lanes keep the
@@ -658,6 +689,7 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             for (int k = 0; k < cn; k++) cudaMemcpyAsync(ho[k], co[k], nb, cudaMemcpyDeviceToHost, sd);
             g_d2h_bytes += (unsigned long long)cn * nb;
             cudaEventRecord(ev_d2h_[s], sd);
+            if (trace) { cudaEventRecord(tr.back().c, sd); host_issue.push_back(host_ms()); }
             used[s] = 1;
             cn = 0;
             chunk++;
@@ -668,6 +700,18 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
     cudaError_t e = cudaStreamSynchronize(st_copy_[0]);
     for (Lane* L : lanes_) { cudaError_t e2 = cudaStreamSynchronize(L->st); if (e2 != cudaSuccess) e = e2; }
     for (int k = 1; k < 3; k++) { cudaError_t e3 = cudaStreamSynchronize(st_copy_[k]); if (e3 != cudaSuccess) e = e3; }
+    if (trace && !tr.empty()) {
+        fprintf(stderr, "[rife_b200 trace] process_batch n=%d: chunk lane | compute start..end | d2h end (ms since the first chunk's start) | host issued at\n", n);
+        for (size_t i = 0; i < tr.size(); i++) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tr[0].a, tr[i].a); cudaEventElapsedTime(&b, tr[0].a, tr[i].b); cudaEventElapsedTime(&c, tr[0].a, tr[i].c);
+            fprintf(stderr, "[rife_b200 trace] %2zu %d | %7.2f .. %7.2f | %7.2f | %7.2f\n", i, tr[i].lane, a, b, c, i < host_issue.size() ? host_issue[i] : -1.0);
+        }
+        for (auto& t : tr) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); cudaEventDestroy(t.c); }
+        cudaGetLastError();
+        fprintf(stderr, "[rife_b200 trace] chunk 0 on the host: uploads queued %.2f, waits queued %.2f, kernels queued %.2f ms\n", tr_first[0], tr_first[1], tr_first[2]);
+        fprintf(stderr, "[rife_b200 trace] call returned after %.2f ms on the host\n", host_ms());
+    }
     for (auto& f : frames_) { f.reading = false; if (!frame_cache_ || rc) f.host = nullptr; }
     if (rc) { cudaGetLastError(); return rc; }
     if (e != cudaSuccess) { set_error(std::string("CUDA failure: ") + cudaGetErrorString(e)); return -2; }

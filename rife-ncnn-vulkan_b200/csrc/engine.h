@@ -136,6 +136,7 @@ private:
     int frame_cache_ = 0;
     unsigned long long frame_hits_ = 0;
     FrameEntry* frame_lookup(const uint8_t* host, size_t nb, FrameEntry* const* cur, int ncur, bool* hit);
+    void frames_fit(size_t nb);
     // Pinned staging for process() calls that arrive with pageable buffers (what the reference CLI passes: stb_image / malloc
     // memory, src/main.cpp:140-187): every caller thread copies its own frames into a pinned slot BEFORE it queues, and its result
     // out of the slot afterwards, so the copies of concurrent callers run in parallel on their own cores and the thread that
