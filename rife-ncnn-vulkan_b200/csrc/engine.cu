@@ -680,9 +680,8 @@ int Engine::process_batch(int n, const uint8_t* const* in0, const uint8_t* const
             if (trace) cudaEventRecord(tr.back().b, L.st);
             cudaEventRecord(ev_comp_[s], L.st);
             for (int u = 0; u < nfe; u++) { cudaEventRecord(fe[u]->read_done, L.st); fe[u]->reading = true; }
-            // results go home either on the lane's own stream (the copy sits between this lane's chunks while the other lanes keep the
-            // GPU busy; no cross-stream hand-over on the critical path) or on two dedicated copy streams (RIFE_B200_D2H=0, and always
-            // with a single lane, where the first form would serialise copy and compute)
+            // results go home on two dedicated copy streams (default), or on the lane's own stream (RIFE_B200_D2H=1: no cross-stream
+            // hand-over, but the lane's next chunk then waits for the copy; never with a single lane)
             const bool on_lane = d2h_on_lane_ && nl > 1;
             cudaStream_t sd = on_lane ? L.st : st_copy_[1 + (chunk & 1)];
             if (!on_lane) cudaStreamWaitEvent(sd, ev_comp_[s], 0);

@@ -98,7 +98,8 @@ private:
     int combine_ = COMBINE_DEFAULT;  // concurrent process() calls on this handle are executed as one lock-step batch (combiner.h)
     int cpu_crop_quirk_ = 0;  // 1: reproduce the reference CPU path's contiguous read of the padded output (rife.cpp:4375-4387)
     int head_pack_ = HEAD_PACK_DEFAULT;  // fused path: packed block-head tensors (fused_v46_kernels.cuh)
-    int d2h_on_lane_ = 1;     // process_batch: device -> host copies of a chunk's results on the lane's own stream (RIFE_B200_D2H)
+    int d2h_on_lane_ = 0;     // process_batch: 1 = a chunk's results go home on the lane's own stream instead of the two copy streams
+                              // (RIFE_B200_D2H; measured 2 % slower at 1080p, equal at 4K: profiles/README.md, session 19)
     int bgr_ = 0;             // frames are B,G,R in memory (the reference's Windows build: rife_preproc.comp:13,53-56)
     Combiner<HostReq> combiner_;
     int run_combined(HostReq** rq, int n);
