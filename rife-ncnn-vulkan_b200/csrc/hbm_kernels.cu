@@ -157,21 +157,32 @@ __global__ void __launch_bounds__(256, 3) postproc_tta_kernel(PostArgs pa, int w
         float mean[NSET][4];
 #pragma unroll
         for (int s = 0; s < NSET; s++) {
-            __syncthreads();
+            // all eight 16-byte loads of this (channel, set) are issued before anything waits: the row-major four stay in
+            // registers across the barrier (four loads in flight per thread left the kernel latency-bound at 37 % occupancy)
+            float4 rv[4], tv[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {  // y = y0 + a, x = x0 + b4 .. + 3
+                const bool rf = o == 1 || o == 2, rs = o == 2 || o == 3;
+                const size_t si = (size_t)(rs ? hp - 1 - (y0 + a) : y0 + a) * wp + (rf ? wp - 4 - (x0 + b4) : x0 + b4);
+                rv[o] = *reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si);
+            }
 #pragma unroll
             for (int o = 4; o < 8; o++) {  // x = x0 + a (slow axis of the [wp][hp] plane), y = y0 + b4 .. + 3 (fast)
                 const bool rf = o == 5 || o == 6, rs = o == 6 || o == 7;
                 const size_t si = (size_t)(rs ? wp - 1 - (x0 + a) : x0 + a) * hp + (rf ? hp - 4 - (y0 + b4) : y0 + b4);
-                const float4 v = rev4(*reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si), rf);
+                tv[o - 4] = *reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int o = 4; o < 8; o++) {
+                const float4 v = rev4(tv[o - 4], o == 5 || o == 6);
                 T[o - 4][a][b4] = v.x; T[o - 4][a][b4 + 1] = v.y; T[o - 4][a][b4 + 2] = v.z; T[o - 4][a][b4 + 3] = v.w;
             }
             __syncthreads();
             float sum[4] = {0.f, 0.f, 0.f, 0.f};  // rife.cpp:4060-4144: the eight values are added in orientation order, then / 8
 #pragma unroll
-            for (int o = 0; o < 4; o++) {  // y = y0 + a, x = x0 + b4 .. + 3
-                const bool rf = o == 1 || o == 2, rs = o == 2 || o == 3;
-                const size_t si = (size_t)(rs ? hp - 1 - (y0 + a) : y0 + a) * wp + (rf ? wp - 4 - (x0 + b4) : x0 + b4);
-                const float4 v = rev4(*reinterpret_cast<const float4*>(pa.in[s * 8 + o] + q * plane + si), rf);
+            for (int o = 0; o < 4; o++) {
+                const float4 v = rev4(rv[o], o == 1 || o == 2);
                 sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
             }
 #pragma unroll
@@ -250,9 +261,10 @@ __global__ void temporal_merge_v2_kernel(float* __restrict__ f, float* __restric
     constexpr int L = sizeof(V) / 4;
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * L;
     if (i >= n) return;
-    V F[4], R[4];
+    V F[4], R[4], a, b;
 #pragma unroll
     for (int c = 0; c < 4; c++) { F[c] = *reinterpret_cast<const V*>(f + c * n + i); R[c] = *reinterpret_cast<const V*>(fr + c * n + i); }
+    if (has_mask) { a = *reinterpret_cast<const V*>(f + 4 * n + i); b = *reinterpret_cast<const V*>(fr + 4 * n + i); }  // all ten loads in flight before the first store
     V X, Y, Z, W;
 #pragma unroll
     for (int j = 0; j < L; j++) {
@@ -264,7 +276,6 @@ __global__ void temporal_merge_v2_kernel(float* __restrict__ f, float* __restric
     *reinterpret_cast<V*>(f + i) = X; *reinterpret_cast<V*>(f + n + i) = Y; *reinterpret_cast<V*>(f + 2 * n + i) = Z; *reinterpret_cast<V*>(f + 3 * n + i) = W;
     *reinterpret_cast<V*>(fr + i) = Z; *reinterpret_cast<V*>(fr + n + i) = W; *reinterpret_cast<V*>(fr + 2 * n + i) = X; *reinterpret_cast<V*>(fr + 3 * n + i) = Y;
     if (has_mask) {
-        V a = *reinterpret_cast<const V*>(f + 4 * n + i), b = *reinterpret_cast<const V*>(fr + 4 * n + i);
 #pragma unroll
         for (int j = 0; j < L; j++) {
             const float m = (reinterpret_cast<float*>(&a)[j] - reinterpret_cast<float*>(&b)[j]) * 0.5f;
@@ -481,12 +492,16 @@ void launch_flow_tta_avg(float* const* f8, int nch, int fw, int fh, cudaStream_t
 // gathers of the group are all issued before the first use (the warp's lanes walk neighbouring pixels, so for a smooth
 // flow each gather instruction touches one or two 128-byte lines); stores are full coalesced lines.
 // ------------------------------------------------------------------------------------------------
-template <int CG>
+// Address arithmetic was most of this kernel (43 LEA + 36 IADD3 of 240 SASS instructions for 3 channels: every gather formed
+// its 64-bit address from scratch); now the four tap pointers are formed once and stepped plane by plane with one IMAD.WIDE
+// each (the empty asm keeps the compiler from folding the steps back into per-load index arithmetic): 3 ch 187 -> ~115
+// executed instructions per pixel.  FULL = all CG channels of the group exist (no per-channel predicate).
+template <int CG, bool FULL>
 __global__ void __launch_bounds__(128) warp_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out, int c, int h, int w) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const int hw = h * w, pi = y * w + x;  // one plane holds fewer than 2^31 elements (frames up to 32k x 32k / 4)
-    const float sx = x + __ldg(flow + pi), sy = y + __ldg(flow + hw + pi);
+    const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= (unsigned)w) return;
+    const unsigned hw = (unsigned)h * (unsigned)w, pi = y * (unsigned)w + x;  // one plane holds fewer than 2^31 elements (frames up to 32k x 32k / 4)
+    const float sx = (float)(int)x + __ldg(flow + pi), sy = (float)(int)y + __ldg(flow + hw + pi);
     int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
     int x1 = x0 + 1, y1 = y0 + 1;
     x0 = min(max(x0, 0), w - 1);
@@ -494,30 +509,39 @@ __global__ void __launch_bounds__(128) warp_kernel(const float* __restrict__ img
     x1 = min(max(x1, 0), w - 1);
     y1 = min(max(y1, 0), h - 1);
     const float alpha = sx - x0, beta = sy - y0;
-    const int i00 = y0 * w + x0, i01 = y0 * w + x1, i10 = y1 * w + x0, i11 = y1 * w + x1;
+    const unsigned r0 = (unsigned)y0 * (unsigned)w, r1 = (unsigned)y1 * (unsigned)w;
     const int q0 = blockIdx.z * CG;
-    img += (size_t)q0 * hw;
-    out += (size_t)q0 * hw;
+    const float* ib = img + (size_t)q0 * hw;
+    const float* p00 = ib + (r0 + x0);
+    const float* p01 = ib + (r0 + x1);
+    const float* p10 = ib + (r1 + x0);
+    const float* p11 = ib + (r1 + x1);
+    float* po = out + (size_t)q0 * hw + pi;
     float v0[CG], v1[CG], v2[CG], v3[CG];
 #pragma unroll
     for (int j = 0; j < CG; j++) {
-        if (q0 + j < c) {
-            const float* p = img + j * hw;
-            v0[j] = __ldg(p + i00); v1[j] = __ldg(p + i01); v2[j] = __ldg(p + i10); v3[j] = __ldg(p + i11);
+        if (FULL || q0 + j < c) {
+            v0[j] = __ldg(p00); v1[j] = __ldg(p01); v2[j] = __ldg(p10); v3[j] = __ldg(p11);
+            asm volatile("" : "+l"(p00), "+l"(p01), "+l"(p10), "+l"(p11));
+            p00 += hw; p01 += hw; p10 += hw; p11 += hw;
         }
     }
 #pragma unroll
     for (int j = 0; j < CG; j++) {
-        if (q0 + j < c) {
+        if (FULL || q0 + j < c) {
             const float v4 = v0[j] * (1 - alpha) + v1[j] * alpha;
             const float v5 = v2[j] * (1 - alpha) + v3[j] * alpha;
-            out[j * hw + pi] = v4 * (1 - beta) + v5 * beta;
+            *po = v4 * (1 - beta) + v5 * beta;
+            po += hw;
         }
     }
 }
 void launch_warp(const float* img, const float* flow, float* out, int c, int h, int w, cudaStream_t st) {
-    if (c <= 4) warp_kernel<4><<<dim3(cdiv(w, 128), h, 1), 128, 0, st>>>(img, flow, out, c, h, w);
-    else warp_kernel<8><<<dim3(cdiv(w, 128), h, cdiv(c, 8)), 128, 0, st>>>(img, flow, out, c, h, w);
+    const dim3 g1(cdiv(w, 128), h, 1);
+    if (c == 3) warp_kernel<3, true><<<g1, 128, 0, st>>>(img, flow, out, c, h, w);
+    else if (c <= 4) warp_kernel<4, false><<<g1, 128, 0, st>>>(img, flow, out, c, h, w);
+    else if (c % 8 == 0) warp_kernel<8, true><<<dim3(cdiv(w, 128), h, c / 8), 128, 0, st>>>(img, flow, out, c, h, w);
+    else warp_kernel<8, false><<<dim3(cdiv(w, 128), h, cdiv(c, 8)), 128, 0, st>>>(img, flow, out, c, h, w);
     g_launch_count++;
 }
 
