@@ -1,7 +1,8 @@
 #!/bin/bash
-O=gpurun_out/r2_s22
+O=gpurun_out/r2_s23
 mkdir -p $O
-timeout 300 python -m pytest tests/test_hbm_kernels_gpu.py -x -q -m gpu 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "tta or v23 or anime or uhd or golden" 2>&1 | tail -3
-timeout 300 python tools/bench_hbm.py --size 1080p > $O/hbm_1080p.txt 2> $O/hbm_1080p.err; grep -v "^{" $O/hbm_1080p.txt | cut -c1-260
-timeout 300 python tools/bench_hbm.py --size 4k > $O/hbm_4k.txt 2> $O/hbm_4k.err; grep -v "^{" $O/hbm_4k.txt | cut -c1-260
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 420 $CS --tool memcheck --error-exitcode 9 --log-file $O/memcheck_hbm.txt python -m pytest tests/test_hbm_kernels_gpu.py -x -q -m gpu > $O/memcheck_hbm_pytest.txt 2>&1; echo "hbm unit tests under memcheck: rc=$?"; tail -2 $O/memcheck_hbm_pytest.txt; tail -3 $O/memcheck_hbm.txt
+timeout 420 $CS --tool memcheck --error-exitcode 9 --log-file $O/memcheck_smoke.txt python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/memcheck_smoke_out.txt 2>&1; echo "smoke (fused v4.6 path, tcgen05 convs) under memcheck: rc=$?"; tail -2 $O/memcheck_smoke_out.txt; tail -3 $O/memcheck_smoke.txt
+timeout 420 $CS --tool memcheck --error-exitcode 9 --log-file $O/memcheck_tta.txt python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "test_tta_modes" > $O/memcheck_tta_pytest.txt 2>&1; echo "TTA parity (generic executor, lanes) under memcheck: rc=$?"; tail -2 $O/memcheck_tta_pytest.txt; tail -3 $O/memcheck_tta.txt
+nvidia-smi --query-gpu=name,memory.used --format=csv,noheader
