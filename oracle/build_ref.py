@@ -176,7 +176,9 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--isa", default="avx2,avx512")
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
-    ap.add_argument("--models", default="rife-v4.6,rife-v4,rife-v2.3,rife-anime")
+    # all eleven model directories the reference ships (src/main.cpp:658-683 sniffs them by name): 440 MB of weights that travel to
+    # the GPU box with oracle/_ref, so `pytest -m gpu` there checks every one of them against the oracle instead of skipping seven
+    ap.add_argument("--models", default="rife-v4.6,rife-v4,rife-v2.3,rife-anime,rife,rife-HD,rife-UHD,rife-v2,rife-v2.4,rife-v3.0,rife-v3.1")
     a = ap.parse_args()
     if not os.path.isdir(a.ref):
         print("build_ref: %s absent -- keeping prebuilt oracle/_ref as is" % a.ref)

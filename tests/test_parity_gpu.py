@@ -375,8 +375,13 @@ def test_every_model_directory_vs_oracle(pkg, model):
 
 @pytest.mark.parametrize("model,uhd", [("rife-UHD", True), ("rife-v3.1", True), ("rife-HD", False)])
 def test_more_models_with_tta(pkg, model, uhd):
+    """UHD cases use a size whose halves are multiples of 32: the reference's CPU path pads to 32 also in UHD mode
+    (rife.cpp:1238-1240), halves the padded frame and runs the flownet on it (rife.cpp:2212-2228); at 160x96 the 80x48 input makes
+    the flownet's pyramid levels disagree in size and the reference binary (and the restatement, faithfully) corrupts its heap --
+    there is no reference output to compare with."""
     _need(model)
-    _ok(parity.check_case(pkg, model, 160, 96, tta=True, tta_temporal=True, uhd=uhd))
+    w, h = (192, 128) if uhd else (160, 96)
+    _ok(parity.check_case(pkg, model, w, h, tta=True, tta_temporal=True, uhd=uhd))
 
 
 @pytest.mark.parametrize("model,fast", [("rife-v4.6", 1), ("rife-v4.6", 0), ("rife-v4", 1), ("rife-v2.3", 0)])
