@@ -585,7 +585,7 @@ def main():
                 "config": {"workload": desc if args.model == MODEL else desc.replace("rife-v4.6", args.model), "timestep": args.timestep, "tta": args.tta,
                            "tta_temporal": args.tta_temporal, "pairs_per_step": head["pairs_per_step_all_ranks"], "precision_tier": args.precision, "lanes": args.lanes, "batch": args.batch,
                            "images_per_lockstep_batch": head["kb"], "plain_fp16_blocks_mask": eng.get_option("plain_blocks"), "recompute_fm": eng.get_option("recompute_fm"), "head_pack": eng.get_option("head_pack"),
-                           "wide_tiles": int(os.environ.get("RIFE_B200_WIDE", "1")),
+                           "wide_tiles": int(os.environ.get("RIFE_B200_WIDE", "0")),  # library default TC_WIDE_DEFAULT = 0 (csrc/tc_conv.h)
                            "fused_path": head["fast"], "l2": "flushed between timed steps (256 MiB memset)", "weights": "reference model files" if "_ref" in md else "synthetic",
                            "host_numa": numa, "host_link_GBps": link},
                 "gflop_per_frame": hb["gflop_per_frame"], "model_tflops": hb["value"] * GFLOP_PER_FRAME[args.workload] / 1000.0 if plain_v46 else None,
