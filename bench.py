@@ -44,7 +44,9 @@ GFLOP_PER_FRAME = {"1080p": 175.2, "4k": 701.0}
 PAIRS_DEFAULT = {"1080p": 128, "4k": 32}
 STRONG_STREAM = {"1080p": 1024, "4k": 256}       # --scaling strong: pairs of the one fixed stream
 PAIRS_ENV = int(os.environ.get("RIFE_BENCH_PAIRS", "0"))  # profiling runs shrink the step
-DISTINCT_FRAMES = 9  # consecutive frames of the synthetic stream; pairs cycle through them
+DISTINCT_FRAMES = 129  # consecutive frames of the synthetic stream: the default steps (128 / 32 pairs) never send a frame twice as
+# a NEW frame -- pair i is (frame i, frame i + 1), so the host-buffer leg uploads pairs + 1 distinct frames per step, what a real
+# stream needs (with 9 cycling frames, as until round 2, the library's per-call frame table reduced the upload to 9 frames)
 MODEL = "rife-v4.6"
 
 
@@ -259,7 +261,7 @@ def measure(ctx, workload, args, headline):
     # synthetic frames: a short stream (distinct per rank under weak scaling; one shared stream under strong scaling)
     nframes = min(max(pairs, 1), DISTINCT_FRAMES - 1) + 1
     seed = rank if args.scaling == "weak" else 0
-    frames = [parity.synth.frame(first_pair + k, w, h, seed=seed) for k in range(nframes)]
+    frames = parity.synth.stream(first_pair, nframes, w, h, seed=seed)
     host = [torch.from_numpy(f).pin_memory() for f in frames]
     dev = [t.cuda(non_blocking=True) for t in host]
     out_dev = [torch.empty_like(dev[0]) for _ in range(pairs)]

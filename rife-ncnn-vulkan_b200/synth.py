@@ -32,3 +32,29 @@ def frame(k, w, h, dx=3, dy=2, seed=0):
 
 def pair(w, h, k=0, dx=3, dy=2, seed=0):
     return frame(k, w, h, dx, dy, seed), frame(k + 1, w, h, dx, dy, seed)
+
+
+def stream(k0, n, w, h, dx=3, dy=2, seed=0):
+    """Frames k0 .. k0 + n - 1 of the stream, bit-identical to frame(k, ...): the stream is one pattern translating by whole
+    pixels, so every frame is a window of ONE canvas (computed once: n frames for the price of about one and a half)."""
+    if n <= 0:
+        return []
+    kmax = k0 + n - 1
+    adx, ady = abs(dx) * (n - 1), abs(dy) * (n - 1)
+    # canvas[Y, X] = pattern(X - X0, Y - Y0) with (X0, Y0) chosen so that every frame's window starts at a non-negative offset
+    ys, xs = np.meshgrid(np.arange(h + ady, dtype=np.int64), np.arange(w + adx, dtype=np.int64), indexing="ij")
+    ox = dx * kmax if dx >= 0 else dx * k0
+    oy = dy * kmax if dy >= 0 else dy * k0
+    xs = xs - ox + 100003 * (seed + 1)
+    ys = ys - oy + 100019 * (seed + 1)
+    canvas = np.empty((h + ady, w + adx, 3), np.uint8)
+    for c in range(3):
+        base = 0.5 + 0.4 * np.sin(0.05 * xs + c) * np.cos(0.07 * ys)
+        n_ = ((_hash32(c, ys >> 2, xs >> 2) >> np.uint64(9)) & np.uint64(255)).astype(np.float64) / 255.0 * 0.10 - 0.05
+        v = np.clip(base + n_, 0.0, 1.0)
+        canvas[:, :, c] = np.floor(v * 255.0 + 0.5).astype(np.uint8)
+    out = []
+    for k in range(k0, k0 + n):
+        x0, y0 = ox - dx * k, oy - dy * k  # frame k reads the pattern at (x - dx k, y - dy k) = canvas column x + (ox - dx k)
+        out.append(np.ascontiguousarray(canvas[y0:y0 + h, x0:x0 + w]))
+    return out

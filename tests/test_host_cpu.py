@@ -34,3 +34,15 @@ def test_family_flags_match_reference_sniffing(pkg):
     assert pkg.family_flags("rife-v3.1") == (True, False)
     assert pkg.family_flags("rife-anime") == (False, False)
     assert pkg.family_flags("rife-HD/") == (False, False)
+
+
+def test_synth_stream_equals_frame_by_frame():
+    """bench.py builds its frame stream from one canvas (synth.stream); it must be the frames synth.frame defines."""
+    import numpy as np
+    import parity
+    for k0, n, w, h, dx, dy, seed in ((0, 9, 64, 48, 3, 2, 0), (5, 7, 70, 50, 3, 2, 1), (2, 5, 64, 48, -3, 2, 0), (0, 4, 33, 31, 24, 16, 2), (3, 3, 40, 40, 0, 0, 0)):
+        fr = parity.synth.stream(k0, n, w, h, dx, dy, seed)
+        assert len(fr) == n
+        for i in range(n):
+            assert np.array_equal(fr[i], parity.synth.frame(k0 + i, w, h, dx, dy, seed)), (k0, i)
+            assert fr[i].flags["C_CONTIGUOUS"]

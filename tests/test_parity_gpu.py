@@ -462,6 +462,37 @@ def test_frame_cache_reuses_uploads_across_calls(pkg):
     assert np.array_equal(again, want)
 
 
+def test_long_stream_recycles_the_frame_table(pkg):
+    """One process_batch call with more distinct frames (141) than the frame table holds (66): entries are recycled while lanes
+    still read earlier chunks (an upload into a recycled entry waits for the lane that read it).  Every result must equal the
+    single-call result for the same pair, bit for bit; then a call with a larger frame size on the same handle (the table drops
+    its undersized buffers in one go), and the first size again."""
+    _need("rife-v4.6")
+    w, h = 160, 96
+    n = 140
+    frames = parity.synth.stream(0, n + 1, w, h)
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    r.load(parity.model_dir("rife-v4.6"))
+    outs = [np.empty_like(frames[0]) for _ in range(n)]
+    ts = [0.5 if i % 3 else 0.25 for i in range(n)]
+    h2d0 = pkg.copy_bytes()[0]
+    r.process_batch_ptr([f.ctypes.data for f in frames[:n]], [f.ctypes.data for f in frames[1:]], w, h, ts, [o.ctypes.data for o in outs])
+    assert pkg.copy_bytes()[0] - h2d0 == (n + 1) * w * h * 3  # every frame of the stream went up exactly once
+    for i in (0, 1, 7, 8, 63, 64, 65, 66, 67, 100, 131, 132, n - 1):
+        assert np.array_equal(outs[i], r.process(frames[i], frames[i + 1], ts[i])), i
+    w2, h2 = 256, 192
+    big = parity.synth.stream(0, 12, w2, h2)
+    outs2 = [np.empty_like(big[0]) for _ in range(11)]
+    r.process_batch_ptr([f.ctypes.data for f in big[:11]], [f.ctypes.data for f in big[1:]], w2, h2, [0.5] * 11, [o.ctypes.data for o in outs2])
+    for i in (0, 5, 10):
+        assert np.array_equal(outs2[i], r.process(big[i], big[i + 1], 0.5)), i
+    outs3 = [np.empty_like(frames[0]) for _ in range(n)]
+    r.process_batch_ptr([f.ctypes.data for f in frames[:n]], [f.ctypes.data for f in frames[1:]], w, h, ts, [o.ctypes.data for o in outs3])
+    r.close()
+    for a_, b_ in zip(outs, outs3):
+        assert np.array_equal(a_, b_)
+
+
 def test_failed_reload_leaves_the_engine_usable(pkg):
     """load_packed with a damaged blob on a loaded engine must fail without touching the loaded model (transactional load)."""
     _need("rife-v4.6")
