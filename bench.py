@@ -418,7 +418,7 @@ def e2e_process_block(ctx, workload, args):
     eng = ctx.eng
     out = {}
     nf = 9
-    frames = [parity.synth.frame(k, w, h, seed=3) for k in range(nf)]
+    frames = parity.synth.stream(0, nf, w, h, seed=3)
     for kind in ("pinned", "pageable"):
         if kind == "pinned":
             hold = [torch.from_numpy(f).pin_memory() for f in frames]
