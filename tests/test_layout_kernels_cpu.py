@@ -58,12 +58,12 @@ def _c8_ref(x, cpad, split, s2d):
     return np.stack([lay(hi), lay(lo)]) if split else lay(hi)[None]
 
 
-@pytest.mark.parametrize("c,cpad,h,w", [(12, 16, 6, 10), (7, 16, 4, 6), (64, 64, 5, 9), (8, 8, 2, 2), (3, 8, 8, 12)])
+_SHAPES = [(12, 16, 6, 10), (7, 16, 4, 6), (64, 64, 5, 9), (8, 8, 2, 2), (3, 8, 8, 12)]
+
+
+@pytest.mark.parametrize("c,cpad,h,w,s2d", [s + (0,) for s in _SHAPES] + [s + (1,) for s in _SHAPES if s[2] % 2 == 0 and s[3] % 2 == 0])  # space-to-depth: even sizes
 @pytest.mark.parametrize("split", [1, 0])
-@pytest.mark.parametrize("s2d", [0, 1])
-def test_planar_to_c8_and_back(emu, c, cpad, h, w, split, s2d):
-    if s2d and (h % 2 or w % 2):
-        pytest.skip("space-to-depth needs even sizes")
+def test_planar_to_c8_and_back(emu, c, cpad, h, w, s2d, split):
     rng = np.random.default_rng(c * 7 + h)
     x = (rng.standard_normal((c, h, w)) * rng.choice([1e-3, 1.0, 300.0], (c, 1, 1))).astype(np.float32)
     n = cpad * h * w
