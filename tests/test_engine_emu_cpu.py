@@ -1,0 +1,178 @@
+"""The WHOLE engine on the host, against the oracle, without a GPU.  A test-only build links the engine's unmodified host code
+(csrc/capi.cu, engine.cu, exec.cu, model.cpp) with host builds of its plain CUDA kernels (generic_kernels.cu, hbm_kernels.cu:
+a block's threads are real threads, tests/emu/cuda_host_shim.h), a runtime whose device memory is host memory
+(tests/emu/fake_cudart.cpp) and refusing stand-ins for the two tcgen05 pieces (tests/emu/emu_engine_stubs.cpp).  The package
+is pointed at that library (RIFE_B200_LIB) in a child process and runs the same `parity.check_case` the GPU tests run, at
+precision tier 0 (fp32 kernels everywhere): model loading, plan building and arena reuse, Split / Crop aliasing, the fused
+conv epilogues, the v4 and the 3-net pipelines, the orientation fork / join of the TTA modes on helper lanes, staging of pageable
+frames, the frame table -- everything but the tensor-core kernels -- is checked against the reference's own CPU path here.
+Frames are tiny (a host 'block' is 256 OS threads meeting at barriers)."""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "rife-ncnn-vulkan_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+_LAUNCH = re.compile(r"(\w+(?:<[^<>;]*>)?)<<<(.*), (\d+), (\w+), st>>>\((.*)\);")
+
+
+def _cpu_has(flag):
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return flag in line.split(":", 1)[1].split()
+    except OSError:
+        pass
+    return False
+
+
+def _rewrite(src):
+    out, n = _LAUNCH.subn(lambda m: "emu_launch(dim3(%s), %s, %s, [&]() { %s(%s); });" % (m.group(2), m.group(3), m.group(4), m.group(1), m.group(5)), src)
+    assert n == src.count("<<<"), (n, src.count("<<<"))
+    return out
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    inc = "/usr/local/cuda/include"
+    if os.environ.get("CUDA_HOME"):
+        inc = os.path.join(os.environ["CUDA_HOME"], "include")
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("g++ or CUDA headers not available")
+    d = str(tmp_path_factory.mktemp("emu_engine"))
+    gen = _rewrite(open(os.path.join(CSRC, "generic_kernels.cu")).read())
+    assert gen.count("extern __shared__ float smem[];") == 1
+    open(os.path.join(d, "generic_kernels_emu.inc"), "w").write(gen.replace("extern __shared__ float smem[];", "float* smem = reinterpret_cast<float*>(emu_dyn_smem);"))
+    open(os.path.join(d, "hbm_kernels_emu.inc"), "w").write(_rewrite(open(os.path.join(CSRC, "hbm_kernels.cu")).read()))
+    tc = open(os.path.join(CSRC, "tc_conv.cu")).read()
+    a = tc.index("// ---- layout conversion kernels")
+    helpers = [l for l in tc.splitlines() if l.startswith("__device__ __forceinline__ uint32_t pack2(") or l.startswith("int tc_conv_tile_rows(int N)")]
+    assert len(helpers) == 2, helpers
+    open(os.path.join(d, "tc_host_section.inc"), "w").write("\n".join(helpers) + "\n" + _rewrite(tc[a:]))
+    open(os.path.join(d, "tu_generic.cpp"), "w").write('#include "cuda_host_shim.h"\n#include "generic_kernels_emu.inc"\n')
+    open(os.path.join(d, "tu_hbm.cpp"), "w").write('#define EMU_ENGINE_BUILD 1\n#include "cuda_host_shim.h"\n#include "hbm_kernels_emu.inc"\n')
+    flags = ["-O2", "-ffp-contract=off"] + (["-mfma"] if _cpu_has("fma") else []) + ["-std=c++17", "-fPIC", "-pthread", "-w", "-I" + inc, "-I" + CSRC, "-I" + EMU, "-I" + d, "-I" + os.path.join(ROOT, "include")]
+    units = [("tu_generic.cpp", os.path.join(d, "tu_generic.cpp")), ("tu_hbm.cpp", os.path.join(d, "tu_hbm.cpp")), ("stubs", os.path.join(EMU, "emu_engine_stubs.cpp")),
+             ("fake_cudart", os.path.join(EMU, "fake_cudart.cpp"))] + [(f, os.path.join(CSRC, f)) for f in ("capi.cu", "engine.cu", "exec.cu", "model.cpp")]
+    procs = []
+    for name, path in units:
+        obj = os.path.join(d, name.replace(".", "_") + ".o")
+        procs.append((name, obj, subprocess.Popen(["g++"] + flags + ["-x", "c++", "-c", path, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, obj, p in procs:
+        out, _ = p.communicate()
+        assert p.returncode == 0, (name, out[-4000:])
+    so = os.path.join(d, "librife_b200_hostemu.so")
+    r = subprocess.run(["g++", "-shared", "-pthread", "-Wl,--no-undefined", "-o", so] + [o for _, o, _ in procs] + ["-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-6000:]
+    return so
+
+
+_CHILD = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import __graft_entry__ as g
+import parity
+pkg = g.load_package()
+assert pkg.LIB_PATH == %(so)r, pkg.LIB_PATH
+out = []
+for case in json.loads(sys.argv[1]):
+    model, w, h = case.pop("model"), case.pop("w"), case.pop("h")
+    opts = {"precision": 0}
+    opts.update(case.pop("options", {}))
+    res = parity.check_case(pkg, model, w, h, options=opts, **case)
+    out.append(res)
+print("RESULT " + json.dumps(out))
+"""
+
+
+def _run(so, cases, timeout=1500):
+    env = dict(os.environ, RIFE_B200_LIB=so)
+    code = _CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "so": so}
+    r = subprocess.run([sys.executable, "-c", code, json.dumps(cases)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-4000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, r.stdout[-2000:]
+    return json.loads(line[0][7:])
+
+
+def _ok(res):
+    assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["out_std"] > 5, res
+
+
+def test_v4_family_plain(emu_lib):
+    """rife-v4.6 (also a ragged size: the padded result is cropped) and rife-v4 with an off-centre timestep"""
+    for res in _run(emu_lib, [{"model": "rife-v4.6", "w": 64, "h": 64}, {"model": "rife-v4.6", "w": 40, "h": 36, "timestep": 0.3},
+                              {"model": "rife-v4", "w": 64, "h": 32, "timestep": 0.25}]):
+        _ok(res)
+
+
+def test_v46_tta_modes(emu_lib):
+    """-z, and -x -z: eight orientations dealt to helper lanes between the flow-averaging points, 16 inputs to the TTA postproc"""
+    for res in _run(emu_lib, [{"model": "rife-v4.6", "w": 48, "h": 32, "tta_temporal": True}, {"model": "rife-v4.6", "w": 32, "h": 32, "tta": True, "tta_temporal": True}]):
+        _ok(res)
+
+
+def test_three_net_families(emu_lib):
+    """flownet + contextnet + fusionnet: rife-v2.3 (plain and -u), rife-anime (5x5 convolutions, SE blocks)"""
+    for res in _run(emu_lib, [{"model": "rife-v2.3", "w": 64, "h": 64}, {"model": "rife-v2.3", "w": 64, "h": 64, "uhd": True}, {"model": "rife-anime", "w": 32, "h": 32}]):
+        _ok(res)
+
+
+@pytest.mark.skipif(not os.environ.get("RIFE_EMU_FULL"), reason="several minutes on the host; RIFE_EMU_FULL=1 runs it (results of such a run: profiles/README.md)")
+def test_spatial_tta_of_the_three_net_families(emu_lib):
+    for res in _run(emu_lib, [{"model": "rife", "w": 32, "h": 32, "tta": True, "tta_temporal": True}, {"model": "rife-v2.3", "w": 32, "h": 32, "tta": True},
+                              {"model": "rife-v2.3", "w": 32, "h": 32, "tta": True, "tta_temporal": True}], timeout=3000):
+        _ok(res)
+
+
+_API_CHILD = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import __graft_entry__ as g
+import parity
+pkg = g.load_package()
+assert pkg.LIB_PATH == %(so)r
+w, h = 32, 32
+frames = parity.synth.stream(0, 4, w, h)
+r = pkg.RIFE(0, False, False, False, 1, False, True)
+r.load(parity.model_dir("rife-v4.6"))
+r.set_option("precision", 0)
+singles = [r.process(frames[i], frames[i + 1], 0.5) for i in range(3)]
+h2d0 = pkg.copy_bytes()[0]
+outs = [np.empty_like(frames[0]) for _ in range(3)]
+r.process_batch_ptr([f.ctypes.data for f in frames[:3]], [f.ctypes.data for f in frames[1:]], w, h, [0.5, 1.0, 0.5], [o.ctypes.data for o in outs])
+h2d = pkg.copy_bytes()[0] - h2d0
+ok_batch = bool(np.array_equal(outs[0], singles[0]) and np.array_equal(outs[1], frames[2]) and np.array_equal(outs[2], singles[2]))
+r.set_option("frame_cache", 1)
+again = [r.process(frames[i], frames[i + 1], 0.5) for i in range(3)]
+hits = r.get_option("frame_cache_hits")
+err = None
+try:
+    r.process_batch_ptr([frames[0].ctypes.data, 0], [frames[1].ctypes.data, frames[2].ctypes.data], w, h, [0.5, 0.5], [outs[0].ctypes.data, outs[1].ctypes.data])
+except pkg.RifeError as e:
+    err = str(e)
+after = r.process(frames[0], frames[1], 0.5)
+r.close()
+print("RESULT " + json.dumps({"ok_batch": ok_batch, "h2d_frames": h2d / (w * h * 3), "cache_equal": all(bool(np.array_equal(a, b)) for a, b in zip(singles, again)),
+                               "hits": hits, "null_frame_error": err, "usable_after_error": bool(np.array_equal(after, singles[0]))}))
+"""
+
+
+def test_batch_call_frame_table_and_error_path(emu_lib):
+    """process_batch on host buffers (every frame of the call uploaded once, a timestep edge inside the batch), the cross-call frame
+    cache, and a refused call (null frame) that leaves the handle usable -- the engine's host logic, on the host"""
+    env = dict(os.environ, RIFE_B200_LIB=emu_lib)
+    code = _API_CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "so": emu_lib}
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert res["ok_batch"] and res["cache_equal"] and res["usable_after_error"], res
+    assert res["h2d_frames"] == 4 and res["hits"] == 2, res  # pairs (0,1) and (2,3) of the batch: four uploads (the t = 1 pair is a host copy); the cache finds frames 1 and 2 again
+    assert res["null_frame_error"], res
