@@ -42,7 +42,7 @@ static thread_local dim3 blockDim, gridDim;
 // thread and pthread barriers: correct, but a 256-thread barrier costs about a millisecond.)
 // Context switch: on x86-64 six callee-saved registers and the stack pointer (swapcontext costs two sigprocmask system calls per
 // switch, and a barrier of 256 fibers is about a thousand switches); elsewhere ucontext.
-#if defined(__x86_64__)
+#if defined(__x86_64__) && !defined(EMU_NO_FAST_SWITCH)
 #define EMU_FAST_SWITCH 1
 __attribute__((naked, noinline)) static void emu_swap(void** /*save_sp: rdi*/, void* /*load_sp: rsi*/) {
     asm volatile(

@@ -11,9 +11,11 @@
 
 extern "C" {
 
-cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// exact sizes (no slack behind a buffer): under AddressSanitizer an out-of-bounds access of an emulated kernel is then a report
+static void* emu_alloc(size_t n) { void* p = nullptr; return posix_memalign(&p, 256, n ? n : 1) == 0 ? p : nullptr; }
+cudaError_t cudaMalloc(void** p, size_t n) { *p = emu_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void** p, size_t n, unsigned int) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned int) { *p = emu_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaHostAlloc(p, n, 0); }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }

@@ -22,6 +22,25 @@ EMU = os.path.join(ROOT, "tests", "emu")
 _LAUNCH = re.compile(r"(\w+(?:<[^<>;]*>)?)<<<(.*), (\d+), (\w+), st>>>\((.*)\);")
 
 
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    return _build(tmp_path_factory, False)
+
+
+@pytest.fixture(scope="module")
+def emu_lib_asan(tmp_path_factory):
+    if not os.path.exists(_libasan()):
+        pytest.skip("libasan not available")
+    return _build(tmp_path_factory, True)
+
+
+def _libasan():
+    try:
+        return subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
+    except Exception:
+        return ""
+
+
 def _cpu_has(flag):
     try:
         for line in open("/proc/cpuinfo"):
@@ -38,14 +57,13 @@ def _rewrite(src):
     return out
 
 
-@pytest.fixture(scope="module")
-def emu_lib(tmp_path_factory):
+def _build(tmp_path_factory, asan):
     inc = "/usr/local/cuda/include"
     if os.environ.get("CUDA_HOME"):
         inc = os.path.join(os.environ["CUDA_HOME"], "include")
     if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
         pytest.skip("g++ or CUDA headers not available")
-    d = str(tmp_path_factory.mktemp("emu_engine"))
+    d = str(tmp_path_factory.mktemp("emu_engine_asan" if asan else "emu_engine"))
     gen = _rewrite(open(os.path.join(CSRC, "generic_kernels.cu")).read())
     assert gen.count("extern __shared__ float smem[];") == 1
     open(os.path.join(d, "generic_kernels_emu.inc"), "w").write(gen.replace("extern __shared__ float smem[];", "float* smem = reinterpret_cast<float*>(emu_dyn_smem);"))
@@ -57,7 +75,10 @@ def emu_lib(tmp_path_factory):
     open(os.path.join(d, "tc_host_section.inc"), "w").write("\n".join(helpers) + "\n" + _rewrite(tc[a:]))
     open(os.path.join(d, "tu_generic.cpp"), "w").write('#include "cuda_host_shim.h"\n#include "generic_kernels_emu.inc"\n')
     open(os.path.join(d, "tu_hbm.cpp"), "w").write('#define EMU_ENGINE_BUILD 1\n#include "cuda_host_shim.h"\n#include "hbm_kernels_emu.inc"\n')
-    flags = ["-O2", "-ffp-contract=off"] + (["-mfma"] if _cpu_has("fma") else []) + ["-std=c++17", "-fPIC", "-pthread", "-w", "-I" + inc, "-I" + CSRC, "-I" + EMU, "-I" + d, "-I" + os.path.join(ROOT, "include")]
+    # AddressSanitizer build: device memory is the (exact-size) host heap; fibers switch through ucontext there (ASan follows
+    # swapcontext, not a hand-written switch)
+    asan = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DEMU_NO_FAST_SWITCH"] if asan else []
+    flags = ["-O2", "-ffp-contract=off"] + asan + (["-mfma"] if _cpu_has("fma") else []) + ["-std=c++17", "-fPIC", "-pthread", "-w", "-I" + inc, "-I" + CSRC, "-I" + EMU, "-I" + d, "-I" + os.path.join(ROOT, "include")]
     units = [("tu_generic.cpp", os.path.join(d, "tu_generic.cpp")), ("tu_hbm.cpp", os.path.join(d, "tu_hbm.cpp")), ("stubs", os.path.join(EMU, "emu_engine_stubs.cpp")),
              ("fake_cudart", os.path.join(EMU, "fake_cudart.cpp"))] + [(f, os.path.join(CSRC, f)) for f in ("capi.cu", "engine.cu", "exec.cu", "model.cpp")]
     procs = []
@@ -68,7 +89,7 @@ def emu_lib(tmp_path_factory):
         out, _ = p.communicate()
         assert p.returncode == 0, (name, out[-4000:])
     so = os.path.join(d, "librife_b200_hostemu.so")
-    r = subprocess.run(["g++", "-shared", "-pthread", "-Wl,--no-undefined", "-o", so] + [o for _, o, _ in procs] + ["-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if asan else ["-Wl,--no-undefined"]) + ["-o", so] + [o for _, o, _ in procs] + ["-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-6000:]
     return so
 
@@ -91,11 +112,13 @@ print("RESULT " + json.dumps(out))
 """
 
 
-def _run(so, cases, timeout=1500):
+def _run(so, cases, timeout=1500, asan=False):
     env = dict(os.environ, RIFE_B200_LIB=so)
+    if asan:  # the interpreter is not an ASan build: the runtime has to be loaded first
+        env.update(LD_PRELOAD=_libasan(), ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     code = _CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "so": so}
     r = subprocess.run([sys.executable, "-c", code, json.dumps(cases)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
-    assert r.returncode == 0, r.stdout[-4000:]
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stdout, r.stdout[-4000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
     assert line, r.stdout[-2000:]
     return json.loads(line[0][7:])
@@ -176,3 +199,18 @@ def test_batch_call_frame_table_and_error_path(emu_lib):
     assert res["ok_batch"] and res["cache_equal"] and res["usable_after_error"], res
     assert res["h2d_frames"] == 4 and res["hits"] == 2, res  # pairs (0,1) and (2,3) of the batch: four uploads (the t = 1 pair is a host copy); the cache finds frames 1 and 2 again
     assert res["null_frame_error"], res
+
+
+def test_address_sanitizer_build(emu_lib_asan):
+    """The same host build under AddressSanitizer.  Device allocations are exact-size heap blocks there, so an access of an
+    emulated kernel or of the engine's host code past an ALLOCATION -- a frame, a per-lane buffer, a weight blob, an executor arena
+    as a whole (tensors inside one arena are not separated) -- is a report (checked by injection: a postproc that writes its last
+    row 4 bytes late aborts with heap-buffer-overflow).  A ragged frame through the v4 pipeline -- partial tiles in every kernel --
+    must finish without a report and still match the oracle.  RIFE_EMU_FULL=1 adds
+    the TTA, UHD and 3-net cases (10+ minutes; a clean run of all of them is recorded in profiles/README.md)."""
+    cases = [{"model": "rife-v4.6", "w": 40, "h": 36, "timestep": 0.3}]
+    if os.environ.get("RIFE_EMU_FULL"):
+        cases += [{"model": "rife-v4.6", "w": 32, "h": 32, "tta": True, "tta_temporal": True}, {"model": "rife-v2.3", "w": 64, "h": 64, "uhd": True},
+                  {"model": "rife-anime", "w": 32, "h": 32}, {"model": "rife-v2.3", "w": 32, "h": 32, "tta": True, "tta_temporal": True}]
+    for res in _run(emu_lib_asan, cases, timeout=3600, asan=True):
+        _ok(res)
