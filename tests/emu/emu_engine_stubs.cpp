@@ -7,7 +7,18 @@
 
 #include "fused_v46.h"
 #include "kernels.h"
+#include "rife_b200.h"
 #include "tc_conv.h"
+
+// The host build has no tensor cores, so a handle starts at precision tier 0 (fp32 kernels) instead of tier 1: capi.cu is compiled
+// with -Drife_b200_create=rife_b200_create_tier1 and this is the exported constructor.  (A caller that cannot set options -- the
+// reference's CLI -- then works against the host build too.)
+extern "C" int rife_b200_create_tier1(rife_b200_t** handle, int gpuid, int tta_mode, int tta_temporal_mode, int uhd_mode, int num_threads, int rife_v2, int rife_v4);
+extern "C" int rife_b200_create(rife_b200_t** handle, int gpuid, int tta_mode, int tta_temporal_mode, int uhd_mode, int num_threads, int rife_v2, int rife_v4) {
+    const int r = rife_b200_create_tier1(handle, gpuid, tta_mode, tta_temporal_mode, uhd_mode, num_threads, rife_v2, rife_v4);
+    if (r == 0) rife_b200_set_option(*handle, "precision", 0);
+    return r;
+}
 
 namespace rife {
 

@@ -84,7 +84,8 @@ def _build(tmp_path_factory, asan):
     procs = []
     for name, path in units:
         obj = os.path.join(d, name.replace(".", "_") + ".o")
-        procs.append((name, obj, subprocess.Popen(["g++"] + flags + ["-x", "c++", "-c", path, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        extra = ["-Drife_b200_create=rife_b200_create_tier1"] if name == "capi.cu" else []  # see tests/emu/emu_engine_stubs.cpp
+        procs.append((name, obj, subprocess.Popen(["g++"] + flags + extra + ["-x", "c++", "-c", path, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, obj, p in procs:
         out, _ = p.communicate()
         assert p.returncode == 0, (name, out[-4000:])
@@ -214,3 +215,44 @@ def test_address_sanitizer_build(emu_lib_asan):
                   {"model": "rife-anime", "w": 32, "h": 32}, {"model": "rife-v2.3", "w": 32, "h": 32, "tta": True, "tta_temporal": True}]
     for res in _run(emu_lib_asan, cases, timeout=3600, asan=True):
         _ok(res)
+
+
+def test_reference_cli_on_the_host_build(emu_lib, tmp_path):
+    """The reference's UNMODIFIED src/main.cpp linked against the `class RIFE` shim (host/_cli/rife-b200-cli, built by build() when
+    /root/reference is present), in directory mode with its load / proc / save threads (`-j 1:2:2`: two threads call RIFE::process
+    on one handle), against the host build: the drop-in boundary end to end -- dlopen of the library, the ncnn-namespace shim, the
+    request combiner, PNG in and out -- without a GPU.  Every written frame against the oracle (src/main.cpp:712-731 schedule)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    cli = os.path.join(ROOT, "rife-ncnn-vulkan_b200", "host", "_cli", "rife-b200-cli")
+    md = parity.model_dir("rife-v4.6")
+    if not os.path.exists(cli) or md is None or not os.path.exists(os.path.join(md, "flownet.bin")):
+        pytest.skip("host/_cli/rife-b200-cli (needs /root/reference at build time) or the reference model files are missing")
+    try:
+        from PIL import Image
+    except Exception:
+        pytest.skip("PIL not available")
+    from test_cli_dropin_gpu import _dir_schedule
+    w, h, count = 32, 24, 3  # w % 32 == 0: for other widths the reference CPU binary shears the frame (DESIGN.md section 2, output crop)
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir()
+    outd.mkdir()
+    frames = parity.synth.stream(0, count, w, h)
+    for k, f in enumerate(frames):
+        Image.fromarray(f).save(str(ind / ("%08d.png" % (k + 1))))
+    env = dict(os.environ, RIFE_B200_LIB=emu_lib)
+    r = subprocess.run([cli, "-i", str(ind), "-o", str(outd), "-m", md, "-g", "0", "-j", "1:2:2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for i, (sx, t) in enumerate(_dir_schedule(count, 2 * count)):
+        p = outd / ("%08d.png" % (i + 1))
+        assert p.exists(), (i, r.stderr[-1000:])
+        got = np.array(Image.open(str(p)).convert("RGB"))
+        if t == 0.0:
+            assert np.array_equal(got, frames[sx]), i
+        elif t == 1.0:
+            assert np.array_equal(got, frames[sx + 1]), i
+        else:
+            ref, _ = parity.run_oracle("rife-v4.6", frames[sx], frames[sx + 1], t)
+            res = parity.compare(got, ref)
+            assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, (i, sx, t, res)
