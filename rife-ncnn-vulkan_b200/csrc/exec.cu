@@ -226,6 +226,18 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
         if (net.layers[l].type == "Input") { err = "missing input blob " + net.blob_names[b]; return -21; }
         for (int bb : net.layers[l].bottoms) stack.push_back(bb);
     }
+    // 1b. arity: everything below indexes bottoms / tops by position; a damaged .param can name fewer (or more) than the type takes
+    for (int l = 0; l < nl; l++) {
+        if (!need[l]) continue;
+        const Layer& L = net.layers[l];
+        size_t lo = 1, hi = 1;  // bottoms
+        if (L.type == "Concat") hi = (size_t)-1;
+        else if (L.type == "BinaryOp") hi = 2;
+        else if (L.type == "Eltwise" || L.type == "rife.Warp") lo = hi = 2;
+        const bool tops_ok = L.type == "Split" ? L.tops.size() >= 1 : L.tops.size() == 1;
+        if (L.bottoms.size() < lo || L.bottoms.size() > hi || !tops_ok) { err = "wrong number of inputs / outputs for " + L.type + " layer " + L.name; return -23; }
+        if (L.type == "PReLU" && L.slope.empty()) { err = "PReLU without slope data: " + L.name; return -23; }
+    }
     // 2. consumer counts among needed layers (+1 for requested outputs)
     std::vector<int> ncons(nb, 0);
     for (int l = 0; l < nl; l++)
@@ -253,7 +265,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             int c1 = sole_consumer(t);
             if (c1 >= 0 && plan.external_slot[net.layers[c1].tops[0]] < 0) {
                 const Layer& C1 = net.layers[c1];
-                if (C1.type == "PReLU") {
+                if (C1.type == "PReLU" && (C1.slope.size() == 1 || C1.slope.size() == (size_t)std::max(0, L.geti(0, 0)))) {  // (any other slope count is refused by the shape pass)
                     s.fused_act_layer = c1;
                     s.out_blob = C1.tops[0];
                     skipped[c1] = 1;
@@ -362,6 +374,7 @@ int NetRunner::build_plan(const std::vector<std::pair<std::string, Tensor>>& inp
             if (L.bottoms.size() != 2 || L.geti(0, 0) != 1 || !same_shape(in(0), in(1))) { err = "unsupported Eltwise form in " + L.name; return -23; }
             o = in(0);
         } else if (T == "ReLU" || T == "PReLU" || T == "Sigmoid" || T == "Clip" || T == "UnaryOp") {
+            if (T == "PReLU" && L.slope.size() != 1 && (in(0).dims != 3 || L.slope.size() != (size_t)in(0).c)) { err = "PReLU slope count does not match the input channels in " + L.name; return -23; }
             o = in(0);
         } else if (T == "rife.Warp") {
             if (in(1).c < 2 || in(1).h != in(0).h || in(1).w != in(0).w) { err = "Warp shape mismatch in " + L.name; return -23; }

@@ -7,17 +7,35 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include <cuda_runtime.h>
 
 extern "C" {
 
-// exact sizes (no slack behind a buffer): under AddressSanitizer an out-of-bounds access of an emulated kernel is then a report
-static void* emu_alloc(size_t n) { void* p = nullptr; return posix_memalign(&p, 256, n ? n : 1) == 0 ? p : nullptr; }
-cudaError_t cudaMalloc(void** p, size_t n) { *p = emu_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void** p, size_t n, unsigned int) { *p = emu_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// exact sizes (no slack behind a buffer): under AddressSanitizer an out-of-bounds access of an emulated kernel is then a report.
+// Blocks are remembered by kind so that cudaPointerGetAttributes can tell "device", pinned and pageable memory apart.
+static std::mutex g_mu;
+static std::map<const void*, std::pair<size_t, int>> g_blocks;  // start -> (size, 1 = device, 2 = pinned host)
+static void* emu_alloc(size_t n, int kind) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 256, n ? n : 1) != 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_blocks[p] = std::make_pair(n ? n : 1, kind);
+    return p;
+}
+static void emu_free(void* p) {
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(g_mu); g_blocks.erase(p); }
+    free(p);
+}
+cudaError_t cudaMalloc(void** p, size_t n) { *p = emu_alloc(n, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { emu_free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned int) { *p = emu_alloc(n, 2); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaHostAlloc(p, n, 0); }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { emu_free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
@@ -44,9 +62,15 @@ cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* q) {
     memset(a, 0, sizeof *a);
-    a->type = cudaMemoryTypeUnregistered;  // every caller buffer counts as pageable: the staging path is exercised
+    a->type = cudaMemoryTypeUnregistered;  // a caller's own buffer is pageable memory: the engine's staging path is exercised
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_blocks.upper_bound(q);
+    if (it != g_blocks.begin()) {
+        --it;
+        if ((const char*)q < (const char*)it->first + it->second.first) a->type = it->second.second == 1 ? cudaMemoryTypeDevice : cudaMemoryTypeHost;
+    }
     return cudaSuccess;
 }
 

@@ -142,9 +142,27 @@ def test_v46_tta_modes(emu_lib):
         _ok(res)
 
 
-def test_three_net_families(emu_lib):
-    """flownet + contextnet + fusionnet: rife-v2.3 (plain and -u), rife-anime (5x5 convolutions, SE blocks)"""
-    for res in _run(emu_lib, [{"model": "rife-v2.3", "w": 64, "h": 64}, {"model": "rife-v2.3", "w": 64, "h": 64, "uhd": True}, {"model": "rife-anime", "w": 32, "h": 32}]):
+ALL_MODELS = ["rife", "rife-HD", "rife-UHD", "rife-anime", "rife-v2", "rife-v2.3", "rife-v2.4", "rife-v3.0", "rife-v3.1", "rife-v4", "rife-v4.6"]
+
+
+def test_model_families_on_the_host_build(emu_lib):
+    """The model directories the reference ships (src/main.cpp:658-683), one small frame each: flownet + contextnet + fusionnet
+    families with 5x5 convolutions, SE blocks (pooling, inner product, broadcast multiply), PReLU.  By default one directory per
+    graph family (the v4 layouts and rife-v2.3 run in the tests above); RIFE_EMU_FULL=1: all eleven (a run of all eleven: 9 bit-identical,
+    rife-v2 and rife-v3.0 with single 1-LSB flips, 78 / 83 dB)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    pick = ALL_MODELS if os.environ.get("RIFE_EMU_FULL") else ["rife", "rife-HD", "rife-anime", "rife-v2.4", "rife-v3.1"]
+    have = [m for m in pick if parity.model_dir(m)]
+    assert have
+    cases = [dict({"model": m, "w": 32, "h": 32}, **({"timestep": 0.4} if m.startswith("rife-v4") else {})) for m in have]
+    for m, res in zip(have, _run(emu_lib, cases, timeout=3000)):
+        assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50 and res["out_std"] > 5, (m, res)
+
+
+def test_uhd_mode_on_the_host_build(emu_lib):
+    """-u: the flownet runs on the half-size frame, the flow is scaled back up (rife.cpp:2212-2229)"""
+    for res in _run(emu_lib, [{"model": "rife-v2.3", "w": 64, "h": 64, "uhd": True}]):
         _ok(res)
 
 
@@ -256,3 +274,86 @@ def test_reference_cli_on_the_host_build(emu_lib, tmp_path):
             ref, _ = parity.run_oracle("rife-v4.6", frames[sx], frames[sx + 1], t)
             res = parity.compare(got, ref)
             assert res["max_abs_diff"] <= 1 and res["psnr_db"] > 50, (i, sx, t, res)
+
+
+_FUZZ_CHILD = r"""
+import json, os, random, shutil, sys, tempfile
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import __graft_entry__ as g
+import parity
+pkg = g.load_package()
+assert pkg.LIB_PATH == %(so)r
+src = parity.model_dir("rife-v4.6")
+lines = open(os.path.join(src, "flownet.param")).read().splitlines()
+a, b = parity.synth.pair(32, 32)
+TYPES = ["Convolution", "Deconvolution", "BinaryOp", "ReLU", "Concat", "Split", "Crop", "Interp", "PixelShuffle", "Sigmoid", "Eltwise", "rife.Warp", "Input", "PReLU",
+         "InnerProduct", "Pooling"]
+
+
+def mutate(seed):
+    rnd = random.Random(seed)
+    L = list(lines)
+    i = rnd.randrange(2, len(L))
+    tok = L[i].split()
+    kind = rnd.randrange(6)
+    if kind == 0:    # a parameter value
+        idx = [k for k, t in enumerate(tok) if "=" in t and k >= 4]
+        if idx:
+            k = rnd.choice(idx)
+            tok[k] = tok[k].split("=", 1)[0] + "=" + rnd.choice(["0", "-1", "1", "2", "3", "5", "7", "16", "64", "100", "512", "-23310", "1.5"])
+    elif kind == 1:  # a blob reference
+        n = int(tok[2]) + int(tok[3])
+        if n:
+            tok[4 + rnd.randrange(n)] = str(rnd.randrange(0, 276))
+    elif kind == 2:  # the layer type
+        tok[0] = rnd.choice(TYPES)
+    elif kind == 3:
+        tok[2] = str(max(0, int(tok[2]) + rnd.choice([-1, 1])))
+    elif kind == 4:
+        L.pop(i)
+        tok = None
+    else:
+        tok[3] = str(max(0, int(tok[3]) + rnd.choice([-1, 1])))
+    if tok is not None:
+        L[i] = " ".join(tok)
+    return L
+
+
+out = {}
+for seed in json.loads(sys.argv[1]):
+    d = tempfile.mkdtemp()
+    open(os.path.join(d, "flownet.param"), "w").write("\n".join(mutate(seed)) + "\n")
+    os.symlink(os.path.join(src, "flownet.bin"), os.path.join(d, "flownet.bin"))
+    print("SEED %%d" %% seed, flush=True)
+    r = pkg.RIFE(0, False, False, False, 1, False, True)
+    try:
+        r.load(d)
+        try:
+            r.process(a, b, 0.5)
+            out[seed] = "ok"
+        except pkg.RifeError as e:
+            out[seed] = "process refused"
+    except pkg.RifeError as e:
+        out[seed] = "load refused"
+    r.close()
+    shutil.rmtree(d)
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_damaged_graphs_are_refused_not_executed(emu_lib_asan):
+    """One random edit per case to rife-v4.6's flownet.param (a parameter value, a blob reference, a layer type, an input / output
+    count, a dropped line), weights untouched; then load + one frame on the AddressSanitizer host build.  Every case must end in a
+    result or in an error return -- never in a report or a crash.  (This found two reads the plan builder did not guard: a layer
+    with fewer inputs than its type takes -- csrc/exec.cu indexed bottoms by position -- and a PReLU without slope data, whose
+    kernel would have dereferenced a null pointer on the device.)  RIFE_EMU_FULL=1: 400 cases instead of 24."""
+    seeds = list(range(400 if os.environ.get("RIFE_EMU_FULL") else 24))
+    env = dict(os.environ, RIFE_B200_LIB=emu_lib_asan, LD_PRELOAD=_libasan(), ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:allocator_may_return_null=1")
+    code = _FUZZ_CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "so": emu_lib_asan}
+    r = subprocess.run([sys.executable, "-c", code, json.dumps(seeds)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3600)
+    last = [l for l in r.stdout.splitlines() if l.startswith("SEED ")][-1:]
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stdout, (last, r.stdout[-3000:])
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert len(res) == len(seeds)
+    kinds = set(res.values())
+    assert kinds <= {"ok", "process refused", "load refused"} and "process refused" in kinds and "load refused" in kinds, kinds
