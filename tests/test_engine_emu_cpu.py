@@ -357,3 +357,18 @@ def test_damaged_graphs_are_refused_not_executed(emu_lib_asan):
     assert len(res) == len(seeds)
     kinds = set(res.values())
     assert kinds <= {"ok", "process refused", "load refused"} and "process refused" in kinds and "load refused" in kinds, kinds
+
+
+def test_gpu_suite_cases_that_need_no_tensor_cores(emu_lib):
+    """Cases of tests/test_parity_gpu.py that do not depend on the tcgen05 path, run UNCHANGED against the host build (the package
+    takes its library from RIFE_B200_LIB): the t = 0 / 1 copies, the ragged-width crop both ways (the padded-crop default against
+    the restatement and against the zero-padded-by-the-caller property; option cpu_crop_quirk against the reference binary), a null
+    frame inside a batch.  RIFE_EMU_FULL=1 adds the 100x70 and rife-v2.3 variants."""
+    k = "timestep_edges or null_frame or (ragged_widths and 90-50 and not v2.3)"
+    if os.environ.get("RIFE_EMU_FULL"):
+        k = "timestep_edges or null_frame or ragged_widths"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_parity_gpu.py"), "-q", "-m", "gpu", "-k", k, "-p", "no:cacheprovider"],
+                       env=dict(os.environ, RIFE_B200_LIB=emu_lib), cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+    tail = r.stdout.strip().splitlines()[-1]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail and "skipped" not in tail, r.stdout[-3000:]
+    assert int(tail.split(" passed")[0].split()[-1]) >= 5, tail
