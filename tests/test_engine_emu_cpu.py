@@ -372,3 +372,94 @@ def test_gpu_suite_cases_that_need_no_tensor_cores(emu_lib):
     tail = r.stdout.strip().splitlines()[-1]
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail and "skipped" not in tail, r.stdout[-3000:]
     assert int(tail.split(" passed")[0].split()[-1]) >= 5, tail
+
+
+_ABI_CHILD = r"""
+ROOT_DIR, TESTS_DIR = %(root)r, %(tests)r
+import sys, os, ctypes, json
+import numpy as np
+sys.path.insert(0, ROOT_DIR); sys.path.insert(0, TESTS_DIR)
+import __graft_entry__ as g
+import parity
+pkg = g.load_package()
+L = pkg.lib()
+vp = ctypes.c_void_p
+res = {}
+def call(name, fn):
+    print("CALL", name, flush=True)
+    try:
+        res[name] = fn()
+    except Exception as e:
+        res[name] = "py:" + type(e).__name__
+h = vp()
+res["create_cpu"] = L.rife_b200_create(ctypes.byref(h), -1, 0, 0, 0, 1, 0, 1)
+res["create_bad_gpu"] = L.rife_b200_create(ctypes.byref(h), 7, 0, 0, 0, 1, 0, 1)
+res["create_null"] = L.rife_b200_create(None, 0, 0, 0, 0, 1, 0, 1)
+assert L.rife_b200_create(ctypes.byref(h), 0, 0, 0, 0, 1, 0, 1) == 0
+a, b = parity.synth.pair(32, 32)
+o = np.empty_like(a)
+P = lambda x: x.ctypes.data
+call("process_before_load", lambda: L.rife_b200_process(h, P(a), P(b), 32, 32, 0.5, P(o)))
+call("load_null", lambda: L.rife_b200_load(h, None))
+call("load_missing", lambda: L.rife_b200_load(h, b"/nonexistent/dir"))
+call("load_null_handle", lambda: L.rife_b200_load(None, parity.model_dir("rife-v4.6").encode()))
+assert L.rife_b200_load(h, parity.model_dir("rife-v4.6").encode()) == 0
+for name, args in {"w0": (0, 32), "h0": (32, 0), "wneg": (-5, 32), "hneg": (32, -1)}.items():
+    call("process_" + name, lambda args=args: L.rife_b200_process(h, P(a), P(b), args[0], args[1], 0.5, P(o)))
+call("process_null_in0", lambda: L.rife_b200_process(h, None, P(b), 32, 32, 0.5, P(o)))
+call("process_null_out", lambda: L.rife_b200_process(h, P(a), P(b), 32, 32, 0.5, None))
+call("process_null_handle", lambda: L.rife_b200_process(None, P(a), P(b), 32, 32, 0.5, P(o)))
+call("process_nan_t", lambda: L.rife_b200_process(h, P(a), P(b), 32, 32, float("nan"), P(o)))
+call("process_t_out_of_range", lambda: L.rife_b200_process(h, P(a), P(b), 32, 32, 7.5, P(o)))
+arr = (vp * 2)(P(a), P(a)); arrb = (vp * 2)(P(b), P(b)); arro = (vp * 2)(P(o), P(o)); ts = (ctypes.c_float * 2)(0.5, 0.5)
+call("batch_n_negative", lambda: L.rife_b200_process_batch(h, -3, arr, arrb, 32, 32, ts, arro))
+call("batch_n_zero", lambda: L.rife_b200_process_batch(h, 0, arr, arrb, 32, 32, ts, arro))
+call("batch_null_arrays", lambda: L.rife_b200_process_batch(h, 2, None, arrb, 32, 32, ts, arro))
+call("batch_null_ts", lambda: L.rife_b200_process_batch(h, 2, arr, arrb, 32, 32, None, arro))
+v = ctypes.c_int()
+call("get_unknown", lambda: L.rife_b200_get_option(h, b"no_such_option", ctypes.byref(v)))
+call("get_null_key", lambda: L.rife_b200_get_option(h, None, ctypes.byref(v)))
+call("get_null_out", lambda: L.rife_b200_get_option(h, b"lanes", None))
+call("set_unknown", lambda: L.rife_b200_set_option(h, b"no_such_option", 1))
+for key, val in (("lanes", 0), ("lanes", -4), ("lanes", 1000), ("batch", -1), ("batch", 999), ("precision", 9), ("precision", -2), ("plain_blocks", -1), ("recompute_fm", 77)):
+    call("set_%%s_%%d" %% (key, val), lambda key=key, val=val: L.rife_b200_set_option(h, key.encode(), val))
+call("process_after_option_abuse", lambda: L.rife_b200_process(h, P(a), P(b), 32, 32, 0.5, P(o)))
+sz = ctypes.c_size_t()
+call("weights_size_null", lambda: L.rife_b200_weights_size(h, None))
+call("weights_export_small", lambda: (L.rife_b200_weights_size(h, ctypes.byref(sz)), L.rife_b200_weights_export(h, P(o), 16))[1])
+call("load_packed_null", lambda: L.rife_b200_load_packed(h, None, 100))
+call("load_packed_zero", lambda: L.rife_b200_load_packed(h, P(o), 0))
+buf = ctypes.create_string_buffer(8)
+call("stage_report_tiny", lambda: L.rife_b200_stage_report(h, buf, 8))
+call("stage_report_null", lambda: L.rife_b200_stage_report(h, None, 0))
+call("last_error_null", lambda: bool(L.rife_b200_last_error(None) is not None))
+call("forget_null", lambda: L.rife_b200_forget_frames(None))
+call("debug_hbm_bad", lambda: L.rife_b200_debug_hbm(0, None, 9, 32, 32, 3, 0, P(a), None, P(o)))
+call("debug_pack_bad", lambda: L.rife_b200_debug_pack_weights(5, 8, 16, 16, 0, 0, P(o), P(o), 3))
+ok = L.rife_b200_process(h, P(a), P(b), 32, 32, 0.5, P(o))
+res["final_process"] = ok
+L.rife_b200_destroy(h)
+L.rife_b200_destroy(None)
+print("RESULT " + json.dumps(res))
+"""
+
+
+def test_c_abi_refuses_bad_arguments(emu_lib_asan):
+    """Every entry point of include/rife_b200.h with the arguments a careless binding could pass -- null handles and pointers,
+    zero / negative sizes, a missing model directory, process before load, unknown and out-of-range options, undersized export
+    buffers, a damaged packed model -- on the AddressSanitizer host build: an error code every time, no report, and the handle
+    interpolates a frame afterwards."""
+    env = dict(os.environ, RIFE_B200_LIB=emu_lib_asan, LD_PRELOAD=_libasan(), ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:allocator_may_return_null=1")
+    code = _ABI_CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests")}
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    last = [l for l in r.stdout.splitlines() if l.startswith("CALL ")][-1:]
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stdout, (last, r.stdout[-3000:])
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    refused = ["create_cpu", "create_bad_gpu", "create_null", "process_before_load", "load_null", "load_missing", "load_null_handle", "process_w0", "process_h0", "process_wneg",
+               "process_hneg", "process_null_in0", "process_null_out", "process_null_handle", "batch_n_negative", "batch_null_arrays", "batch_null_ts", "get_unknown",
+               "get_null_key", "get_null_out", "set_unknown", "weights_size_null", "weights_export_small", "load_packed_null", "load_packed_zero", "stage_report_null",
+               "forget_null", "debug_hbm_bad", "debug_pack_bad"]
+    for k in refused:
+        assert isinstance(res[k], int) and res[k] < 0, (k, res[k])
+    assert res["create_cpu"] == -1 and res["process_before_load"] == -4 and res["load_missing"] == -3  # the codes include/rife_b200.h documents
+    assert res["batch_n_zero"] == 0 and res["process_after_option_abuse"] == 0 and res["final_process"] == 0 and res["last_error_null"] is True, res
