@@ -152,7 +152,7 @@ def test_model_families_on_the_host_build(emu_lib):
     rife-v2 and rife-v3.0 with single 1-LSB flips, 78 / 83 dB)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import parity
-    pick = ALL_MODELS if os.environ.get("RIFE_EMU_FULL") else ["rife", "rife-HD", "rife-anime", "rife-v2.4", "rife-v3.1"]
+    pick = ALL_MODELS if os.environ.get("RIFE_EMU_FULL") else ["rife-HD", "rife-anime", "rife-v3.1"]
     have = [m for m in pick if parity.model_dir(m)]
     assert have
     cases = [dict({"model": m, "w": 32, "h": 32}, **({"timestep": 0.4} if m.startswith("rife-v4") else {})) for m in have]
