@@ -63,7 +63,9 @@ def _build(tmp_path_factory, asan):
         inc = os.path.join(os.environ["CUDA_HOME"], "include")
     if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
         pytest.skip("g++ or CUDA headers not available")
-    d = str(tmp_path_factory.mktemp("emu_engine_asan" if asan else "emu_engine"))
+    tsan = asan == "tsan"
+    asan = asan is True
+    d = str(tmp_path_factory.mktemp("emu_engine_tsan" if tsan else ("emu_engine_asan" if asan else "emu_engine")))
     gen = _rewrite(open(os.path.join(CSRC, "generic_kernels.cu")).read())
     assert gen.count("extern __shared__ float smem[];") == 1
     open(os.path.join(d, "generic_kernels_emu.inc"), "w").write(gen.replace("extern __shared__ float smem[];", "float* smem = reinterpret_cast<float*>(emu_dyn_smem);"))
@@ -78,6 +80,8 @@ def _build(tmp_path_factory, asan):
     # AddressSanitizer build: device memory is the (exact-size) host heap; fibers switch through ucontext there (ASan follows
     # swapcontext, not a hand-written switch)
     asan = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DEMU_NO_FAST_SWITCH"] if asan else []
+    if tsan:  # ThreadSanitizer over the engine's host threading: kernel launches do nothing (no fibers under TSan), native driver program
+        asan = ["-fsanitize=thread", "-g", "-DEMU_SKIP_KERNELS"]
     flags = ["-O2", "-ffp-contract=off"] + asan + (["-mfma"] if _cpu_has("fma") else []) + ["-std=c++17", "-fPIC", "-pthread", "-w", "-I" + inc, "-I" + CSRC, "-I" + EMU, "-I" + d, "-I" + os.path.join(ROOT, "include")]
     units = [("tu_generic.cpp", os.path.join(d, "tu_generic.cpp")), ("tu_hbm.cpp", os.path.join(d, "tu_hbm.cpp")), ("stubs", os.path.join(EMU, "emu_engine_stubs.cpp")),
              ("fake_cudart", os.path.join(EMU, "fake_cudart.cpp"))] + [(f, os.path.join(CSRC, f)) for f in ("capi.cu", "engine.cu", "exec.cu", "model.cpp")]
@@ -89,6 +93,14 @@ def _build(tmp_path_factory, asan):
     for name, obj, p in procs:
         out, _ = p.communicate()
         assert p.returncode == 0, (name, out[-4000:])
+    if tsan:
+        exe = os.path.join(d, "tsan_engine")
+        r = subprocess.run(["g++"] + flags + ["-fsanitize=thread", "-o", exe, os.path.join(EMU, "tsan_engine_main.cpp")] + [o for _, o, _ in procs] + ["-ldl"],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 and "tsan" in r.stdout:
+            pytest.skip("ThreadSanitizer runtime not available")
+        assert r.returncode == 0, r.stdout[-6000:]
+        return exe
     so = os.path.join(d, "librife_b200_hostemu.so")
     r = subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if asan else ["-Wl,--no-undefined"]) + ["-o", so] + [o for _, o, _ in procs] + ["-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-6000:]
@@ -463,3 +475,16 @@ def test_c_abi_refuses_bad_arguments(emu_lib_asan):
         assert isinstance(res[k], int) and res[k] < 0, (k, res[k])
     assert res["create_cpu"] == -1 and res["process_before_load"] == -4 and res["load_missing"] == -3  # the codes include/rife_b200.h documents
     assert res["batch_n_zero"] == 0 and res["process_after_option_abuse"] == 0 and res["final_process"] == 0 and res["last_error_null"] is True, res
+
+
+def test_engine_threading_under_thread_sanitizer(tmp_path_factory):
+    """tests/emu/tsan_engine_main.cpp: six threads call rife_b200_process on one handle with pageable frames (staging slots, the
+    request combiner, the lock-free option snapshot, per-thread error text) while a seventh flips options and drops the frame cache,
+    on a ThreadSanitizer build of the engine's host code whose kernel launches do nothing.  No report, no failed call."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    exe = _build(tmp_path_factory, "tsan")
+    r = subprocess.run([exe, parity.model_dir("rife-v4.6")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    if r.returncode != 0 and "ThreadSanitizer" not in r.stdout and "TSAN-ENGINE" not in r.stdout:
+        pytest.skip("ThreadSanitizer cannot run in this sandbox: " + r.stdout[-200:])
+    assert r.returncode == 0 and "TSAN-ENGINE failures=0" in r.stdout and "WARNING: ThreadSanitizer" not in r.stdout, r.stdout[-4000:]
